@@ -1,0 +1,76 @@
+"""ctypes binding of libaeqb200.so — the only way arithmetic is reached.
+
+There is deliberately no fallback: if the shared library is missing or a
+symbol cannot be resolved this module raises, and every product entry point
+above it fails with it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaeqb200.so")
+HEADER_PATH = os.path.normpath(
+    os.path.join(_HERE, "..", "..", "include", "aeqb200.h"))
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_L = _c.c_int64
+_F = _c.c_float
+_D = _c.c_double
+
+# name -> (restype, argtypes); must list every function include/aeqb200.h declares
+# (tests/test_cabi_symbols.py parses the header and checks both directions).
+SIGNATURES = {
+    "aeqb_version": (_I, []),
+    "aeqb_last_error": (_c.c_char_p, []),
+    "aeqb_requant_rows_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aeqb_requant_given_minmax_f32":
+        (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "aeqb_requant_blocks_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+}
+
+
+class AeqbError(RuntimeError):
+  """A C-ABI call returned non-zero."""
+
+
+_lib = None
+
+
+def header_functions(path: str = HEADER_PATH) -> list[str]:
+  """Names of all functions declared in the public header."""
+  text = open(path).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+  return sorted(set(re.findall(r"\b(aeqb_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> ctypes.CDLL:
+  """Loads the library once and types every entry point."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python"
+        " ai-edge-quantizer_b200/build.py` (nvcc, sm_100a). aeq_b200 has no"
+        " CPU fallback.")
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, (res, args) in SIGNATURES.items():
+    fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+    fn.restype = res
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+def call(name: str, *args) -> None:
+  """Calls an int-returning entry point and raises AeqbError on failure."""
+  lib = load()
+  rc = getattr(lib, name)(*args)
+  if rc != 0:
+    msg = lib.aeqb_last_error().decode("utf-8", "replace")
+    raise AeqbError(f"{name} failed: {msg}")

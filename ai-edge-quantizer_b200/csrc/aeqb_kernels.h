@@ -1,0 +1,47 @@
+// Internal launcher interface between the C-ABI (aeqb_api.cu) and the kernels.
+// Not installed; the public boundary is include/aeqb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aeqb {
+
+// Per-channel / per-tensor fused requantisation of a [rows, cols] fp32 matrix.
+struct RowsArgs {
+  const float* x;
+  int8_t* q;        // [rows*cols] one value per byte, or null
+  uint8_t* packed;  // [rows*cols*bits/8] INT4 / INT2 packed, or null
+  float* scale;     // [rows] (out_stride 1) or [1] (out_stride 0), or null
+  int32_t* zp;      // same shape as scale, or null
+  const float* clip;       // optional clipping constants, index row*clip_stride
+  const float* given_min;  // optional precomputed min/max (QSV / per-tensor path)
+  const float* given_max;
+  long long rows;
+  int cols;
+  int bits;
+  int symmetric;
+  int mm_stride;    // 0: one min/max for the whole tensor, 1: per row
+  int clip_stride;  // 0 / 1
+  int out_stride;   // 0 / 1
+  int rows_per_tile;  // filled by the launcher
+  long long n_tiles;  // filled by the launcher
+};
+cudaError_t launch_requant_rows(RowsArgs a, int sm_count, cudaStream_t st);
+
+// Blockwise symmetric requantisation of a flat fp32 array cut into `block`-long
+// groups (blocks never straddle rows because cols % block == 0).
+struct BlocksArgs {
+  const float* x;
+  int8_t* q;            // [n] or null
+  uint8_t* packed;      // [n*bits/8] or null (bits 4 only)
+  float* scale;         // [n/block] fp32 (already bf16->fp16 rounded), or null
+  uint16_t* scale_f16;  // [n/block] fp16 bit patterns, or null
+  const float* clip;    // optional [n/block]
+  long long n;
+  int block;
+  int bits;
+  long long n_tiles;  // filled by the launcher
+};
+cudaError_t launch_requant_blocks(BlocksArgs a, int sm_count, cudaStream_t st);
+
+}  // namespace aeqb

@@ -1,0 +1,23 @@
+"""Shared pytest wiring: import paths, the `gpu` marker, oracle access."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "ai-edge-quantizer_b200")):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+  config.addinivalue_line(
+      "markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def cuda():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.fail("-m gpu tests need a CUDA device; aeq_b200 has no CPU fallback")
+  return torch.device("cuda:0")

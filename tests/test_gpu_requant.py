@@ -1,0 +1,95 @@
+"""GPU parity: fused requantisation kernels vs the NumPy oracle, through the C ABI.
+
+Bit-exact bar for integers, packed bytes, scales and zero points (min-max path
+has order-free reductions and IEEE divides only).
+"""
+import numpy as np
+import pytest
+
+from oracle import aeq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x, cuda):
+  import torch
+  return torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+
+
+def _special(w):
+  """Injects the degenerate rows/blocks the reference handles (Appendix A)."""
+  w = w.copy()
+  if w.shape[0] >= 4:
+    w[1, :] = 0.0                      # all-zero row -> scale 1e-9/qmax
+    w[2, : w.shape[1] // 2] = 1e-8     # tiny values: blockwise scale flushes to 0
+    w[3, 0] = 3.0e38                   # huge outlier
+  return w
+
+
+ROW_SHAPES = [(16, 8), (7, 33), (64, 128), (130, 256), (33, 1024), (96, 4096),
+              (5, 8192), (9, 11008), (3, 16384), (2, 16512), (1, 4)]
+
+
+@pytest.mark.parametrize("shape", ROW_SHAPES)
+@pytest.mark.parametrize("bits,symmetric", [(8, True), (8, False), (4, True), (4, False), (2, True)])
+def test_rows_matches_oracle(cuda, shape, bits, symmetric):
+  from aeq_b200 import device
+  w = _special(O.synthetic_weight(*shape, index=shape[1] % 97))
+  ref = O.minmax_requant(w, bits, symmetric)
+  want_packed = bits < 8 and (shape[1] * bits) % 8 == 0
+  out = device.requant_rows(_dev(w, cuda), bits, symmetric, want_packed=want_packed)
+  np.testing.assert_array_equal(out.scale.cpu().numpy(), ref["scale"])
+  np.testing.assert_array_equal(out.zero_point.cpu().numpy(), ref["zero_point"].astype(np.int32))
+  np.testing.assert_array_equal(out.q.cpu().numpy(), ref["q"])
+  if want_packed:
+    np.testing.assert_array_equal(out.packed.cpu().numpy(), O.pack_bits(bits, ref["q"]))
+
+
+@pytest.mark.parametrize("shape", [(4, 32), (16, 64), (64, 256), (33, 2048), (130, 4096), (8, 11008), (3, 16384)])
+@pytest.mark.parametrize("block", [32, 64, 128, 256])
+@pytest.mark.parametrize("bits", [4, 8])
+def test_blocks_matches_oracle(cuda, shape, block, bits):
+  from aeq_b200 import device
+  if shape[1] % block:
+    pytest.skip("cols not divisible by block")
+  w = _special(O.synthetic_weight(*shape, index=block + bits))
+  ref = O.minmax_requant(w, bits, True, block=block)
+  out = device.requant_blocks(_dev(w, cuda), block, bits, want_packed=(bits == 4))
+  np.testing.assert_array_equal(out.scale.cpu().numpy(), ref["scale"])
+  np.testing.assert_array_equal(out.scale_f16.cpu().numpy(), O.blockwise_scale_fp16(ref["scale"]))
+  np.testing.assert_array_equal(out.q.cpu().numpy(), ref["q"])
+  if bits == 4:
+    np.testing.assert_array_equal(out.packed.cpu().numpy(), O.pack_bits(4, ref["q"]))
+
+
+def test_nan_and_inf_rows(cuda):
+  from aeq_b200 import device
+  w = O.synthetic_weight(8, 256, 5)
+  w[0, 3] = np.nan
+  w[1, 7] = np.inf
+  w[2, 9] = -np.inf
+  with np.errstate(all="ignore"):
+    ref = O.minmax_requant(w, 8, True)
+  out = device.requant_rows(_dev(w, cuda), 8, True)
+  np.testing.assert_array_equal(out.scale.cpu().numpy(), ref["scale"])
+  np.testing.assert_array_equal(out.q.cpu().numpy(), ref["q"])
+
+
+def test_unaligned_views(cuda):
+  """Row/column-offset device views take the generic kernels."""
+  import torch
+  from aeq_b200 import device
+  w = O.synthetic_weight(9, 260, 3)
+  flat = torch.empty(w.size + 1, dtype=torch.float32, device=cuda)
+  flat[1:] = _dev(w.reshape(-1), cuda)
+  view = flat[1:].view(9, 260)
+  out = device.requant_rows(view, 8, True)
+  ref = O.minmax_requant(w, 8, True)
+  np.testing.assert_array_equal(out.q.cpu().numpy(), ref["q"])
+  w2 = O.synthetic_weight(5, 256, 4)
+  flat = torch.empty(w2.size + 1, dtype=torch.float32, device=cuda)
+  flat[1:] = _dev(w2.reshape(-1), cuda)
+  out = device.requant_blocks(flat[1:].view(5, 256), 32, 4, want_packed=True)
+  ref = O.minmax_requant(w2, 4, True, block=32)
+  np.testing.assert_array_equal(out.q.cpu().numpy(), ref["q"])
+  np.testing.assert_array_equal(out.packed.cpu().numpy(), O.pack_bits(4, ref["q"]))
