@@ -31,6 +31,14 @@ SIGNATURES = {
     "aeqb_requant_given_minmax_f32":
         (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "aeqb_requant_blocks_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aeqb_minmax_workspace_bytes": (_c.c_size_t, []),
+    "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),
+    "aeqb_row_stats_f32": (_I, [_P, _L, _L, _P, _P, _P, _P]),
+    "aeqb_minmax_blocks_f32": (_I, [_P, _L, _L, _I, _P, _P, _P]),
+    "aeqb_scale_zp_from_minmax": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
+    "aeqb_quantize_f32": (_I, [_P, _L, _L, _L, _P, _P, _I, _I, _I, _P, _P]),
+    "aeqb_dequantize_f32": (_I, [_P, _I, _L, _L, _L, _P, _P, _I, _I, _P, _P]),
+    "aeqb_pack_bits": (_I, [_P, _L, _I, _P, _P]),
 }
 
 

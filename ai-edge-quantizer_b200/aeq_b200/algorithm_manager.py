@@ -1,0 +1,94 @@
+"""Module-level registry instance + the algorithms this package implements.
+
+Mirror of ai_edge_quantizer/algorithm_manager.py:43-75 (exposed functions and
+the `AlgorithmName` keys) with registrations for the weight-carrying ops that
+reach the hot path.  Registration keeps the reference's binding pattern
+(algorithm_manager.py:160-163): `functools.partial(materialize, <alg>.get_tensor_quant_params)`.
+"""
+from __future__ import annotations
+
+import enum
+import functools
+
+from . import algorithm_manager_api
+from . import qtyping
+from .algorithms.uniform_quantize import naive_min_max_quantize
+from .algorithms.utils import common_utils
+from .utils import qsv_utils
+
+_Op = qtyping.TFLOperationName
+
+_alg_manager_instance = algorithm_manager_api.AlgorithmManagerApi()
+
+get_quantization_func = _alg_manager_instance.get_quantization_func
+get_supported_ops = _alg_manager_instance.get_supported_ops
+get_update_qsv_func = _alg_manager_instance.get_update_qsv_func
+get_init_qsv_func = _alg_manager_instance.get_init_qsv_func
+register_op_quant_config_validation_func = (
+    _alg_manager_instance.register_op_quant_config_validation_func)
+register_config_check_policy_func = _alg_manager_instance.register_config_check_policy
+register_quantized_op = _alg_manager_instance.register_quantized_op
+is_op_registered = _alg_manager_instance.is_op_registered
+is_algorithm_registered = _alg_manager_instance.is_algorithm_registered
+check_op_quantization_config = _alg_manager_instance.check_op_quantization_config
+
+
+class AlgorithmName(str, enum.Enum):
+  NO_QUANTIZE = "no_quantize"
+  MIN_MAX_UNIFORM_QUANT = "min_max_uniform_quantize"
+  FLOAT_CASTING = "float_casting"
+  DEQUANTIZED_WEIGHT_RECOVERY = "dequantized_weight_recovery"
+  OCTAV = "OCTAV"
+  HADAMARD_ROTATION = "HADAMARD_ROTATION"
+  DECOMPOSED_HADAMARD_ROTATION = "DECOMPOSED_HADAMARD_ROTATION"
+  MSE = "MSE"
+  GPTQ = "GPTQ"
+  OSCAR = "OSCAR"
+
+
+def _init_qsvs(op_info, graph_info, inputs_to_ignore=None, outputs_to_ignore=None, **kw):
+  """Runtime tensors start without statistics; the first batch is stored verbatim."""
+  del op_info, graph_info, inputs_to_ignore, outputs_to_ignore, kw
+  return {}
+
+
+def _check_config(op_name, op_quant_config, config_check_policy=None):
+  """Blockwise rules of common_utils.check_subchannel_config (:80-101)."""
+  del config_check_policy
+  w = op_quant_config.weight_tensor_config
+  if w is None or not common_utils.is_blockwise(w.granularity):
+    return
+  if op_name not in (_Op.FULLY_CONNECTED, _Op.EMBEDDING_LOOKUP):
+    raise ValueError(f"Unsupported op for blockwise quantization: {op_name}")
+  if op_quant_config.activation_tensor_config is not None:
+    raise ValueError("Blockwise quantization does not support activation tensor quantization.")
+  if not w.symmetric:
+    raise ValueError("Blockwise quantization does not support for asymmetric weight.")
+
+
+# op -> positional inputs that never carry quantisable data
+WEIGHT_OPS = {
+    _Op.FULLY_CONNECTED: (),
+    _Op.CONV_2D: (),
+    _Op.CONV_2D_TRANSPOSE: (0,),   # output-shape tensor
+    _Op.EMBEDDING_LOOKUP: (0,),    # lookup indices
+}
+
+
+def register_weight_algorithm(algorithm_key, get_tensor_quant_params, calibration_func,
+                              update_qsv_func=qsv_utils.moving_average_update):
+  """Binds one algorithm's `get_tensor_quant_params` to every weight-carrying op."""
+  for op_name, ignore in WEIGHT_OPS.items():
+    register_quantized_op(
+        algorithm_key, op_name, _init_qsvs, calibration_func=calibration_func,
+        materialize_func=functools.partial(
+            common_utils.materialize_weight_op, get_tensor_quant_params,
+            inputs_to_ignore=ignore),
+        update_qsv_func=update_qsv_func)
+  register_op_quant_config_validation_func(algorithm_key, _check_config)
+  register_config_check_policy_func(algorithm_key, None)
+
+
+register_weight_algorithm(AlgorithmName.MIN_MAX_UNIFORM_QUANT,
+                          naive_min_max_quantize.get_tensor_quant_params,
+                          naive_min_max_quantize.min_max_calibrate)

@@ -102,3 +102,120 @@ def requant_blocks(x: torch.Tensor, block: int, bits: int,
   _lib.call("aeqb_requant_blocks_f32", _ptr(x), rows, cols, block, bits, _ptr(clip),
             _ptr(q), _ptr(packed), _ptr(scale), _ptr(f16), _stream())
   return Requantized(q, packed, scale, None, f16)
+
+
+# ------------------------------------------------------------------ statistics
+_ws_cache: dict = {}
+
+
+def _minmax_ws(dev: torch.device) -> torch.Tensor:
+  key = (dev.type, dev.index)
+  if key not in _ws_cache:
+    n = _lib.load().aeqb_minmax_workspace_bytes()
+    _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=dev)
+  return _ws_cache[key]
+
+
+def minmax_tensor(x: torch.Tensor, lo: Optional[float] = None,
+                  hi: Optional[float] = None) -> torch.Tensor:
+  """[min, max] of a whole tensor with the (lo, hi) validity filter (aeqb_minmax_tensor_f32)."""
+  if not x.is_cuda or x.dtype != torch.float32:
+    raise ValueError("expected a float32 CUDA tensor")
+  x = x.contiguous()
+  out = torch.empty(2, dtype=torch.float32, device=x.device)
+  _lib.call("aeqb_minmax_tensor_f32", _ptr(x), x.numel(),
+            0.0 if lo is None else float(lo), 0.0 if hi is None else float(hi),
+            int(lo is not None), int(hi is not None), _ptr(out),
+            _ptr(_minmax_ws(x.device)), _stream())
+  return out
+
+
+def row_stats(x: torch.Tensor, want_minmax: bool = True, want_sumsq: bool = False):
+  """Per-row (min, max, sum of squares) of a 2-D tensor; absent outputs are None."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  mk = lambda: torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+  mn, mx = (mk(), mk()) if want_minmax else (None, None)
+  ss = mk() if want_sumsq else None
+  _lib.call("aeqb_row_stats_f32", _ptr(x), rows, cols, _ptr(mn), _ptr(mx), _ptr(ss), _stream())
+  return mn, mx, ss
+
+
+def minmax_blocks(x: torch.Tensor, block: int):
+  """Per-block (min, max), each [rows, cols/block]."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  if cols % block:
+    raise ValueError(
+        f"Quantized dimension {cols} in tensor shape {tuple(x.shape)} is not"
+        f" divisible by block size {block}.")
+  mn = torch.empty((rows, cols // block), dtype=torch.float32, device=x.device)
+  mx = torch.empty_like(mn)
+  _lib.call("aeqb_minmax_blocks_f32", _ptr(x), rows, cols, block, _ptr(mn), _ptr(mx), _stream())
+  return mn, mx
+
+
+# ------------------------------------------------------------------ unfused pieces
+def scale_zp_from_minmax(mn: torch.Tensor, mx: torch.Tensor, bits: int, symmetric: bool,
+                         blockwise: bool, clip: Optional[torch.Tensor] = None):
+  """(zero_point int32, scale fp32, scale_f16 or None), all shaped like `mn`."""
+  mn = mn.contiguous().float()
+  mx = mx.contiguous().float()
+  if clip is not None:
+    clip = clip.contiguous().float()
+  scale = torch.empty_like(mn)
+  zp = torch.empty(mn.shape, dtype=torch.int32, device=mn.device)
+  f16 = torch.empty(mn.shape, dtype=torch.float16, device=mn.device) if blockwise else None
+  _lib.call("aeqb_scale_zp_from_minmax", _ptr(mn), _ptr(mx), _ptr(clip), mn.numel(), bits,
+            int(symmetric), int(blockwise), _ptr(scale), _ptr(zp), _ptr(f16), _stream())
+  return zp, scale, f16
+
+
+def quantize(x: torch.Tensor, scale: torch.Tensor, zp: Optional[torch.Tensor], bits: int,
+             symmetric: bool, channels: int, inner: int) -> torch.Tensor:
+  """clip(rint(x/scale + zp)) with parameters indexed by (i // inner) % channels."""
+  x = x.contiguous()
+  out_dtype = torch.int8 if bits <= 8 else torch.int16
+  q = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+  stride = 0 if scale.numel() == 1 else 1
+  if stride and scale.numel() != channels:
+    raise ValueError(f"scale holds {scale.numel()} values, expected {channels}")
+  if zp is not None:
+    zp = zp.to(torch.int32).contiguous()
+    if zp.numel() != scale.numel():
+      if zp.numel() != 1:
+        raise ValueError(
+            "scale and zero_point must have the same shape or zero_point must have"
+            f" only one element. Got {tuple(scale.shape)} and {tuple(zp.shape)}")
+      zp = zp.reshape(1).expand(scale.numel()).contiguous()
+  _lib.call("aeqb_quantize_f32", _ptr(x), x.numel(), channels, inner,
+            _ptr(scale.contiguous()), _ptr(zp), stride, bits, int(symmetric), _ptr(q), _stream())
+  return q
+
+
+def dequantize(q: torch.Tensor, scale: torch.Tensor, zp: Optional[torch.Tensor],
+               channels: int, inner: int, wrap8: bool = False) -> torch.Tensor:
+  """(q - zp) * scale in fp32."""
+  q = q.contiguous()
+  if q.dtype not in (torch.int8, torch.int16, torch.int32):
+    raise ValueError(f"unsupported quantized dtype {q.dtype}")
+  out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+  stride = 0 if scale.numel() == 1 else 1
+  if zp is not None:
+    zp = zp.to(torch.int32).contiguous()
+    if zp.numel() != scale.numel():
+      zp = zp.reshape(1).expand(scale.numel()).contiguous()
+  _lib.call("aeqb_dequantize_f32", _ptr(q), q.element_size(), q.numel(), channels, inner,
+            _ptr(scale.contiguous()), _ptr(zp), stride, int(wrap8), _ptr(out), _stream())
+  return out
+
+
+def pack_bits(q: torch.Tensor, bits: int) -> torch.Tensor:
+  """INT4 / INT2 packing of a flat int8 tensor (transformation_utils.pack_data)."""
+  if q.dtype not in (torch.int8, torch.uint8):
+    raise ValueError("pack_bits expects int8 / uint8 data")
+  q = q.contiguous().view(torch.int8).reshape(-1)
+  n = q.numel()
+  out = torch.empty((n * bits + 7) // 8, dtype=torch.uint8, device=q.device)
+  _lib.call("aeqb_pack_bits", _ptr(q), n, bits, _ptr(out), _stream())
+  return out

@@ -1,0 +1,93 @@
+"""Drop-in installer: rebinds the REFERENCE's registry to the device kernels.
+
+`install(am)` takes the reference's `ai_edge_quantizer.algorithm_manager`
+module and re-registers every op of every uniform algorithm with the
+reference's own materialiser (all its graph bookkeeping, constraints, bias and
+cache logic stay untouched) partially applied to OUR
+`get_tensor_quant_params` — the exact seam the reference uses itself
+(algorithm_manager.py:160-163, 316-319, 415-418, 446-449; signature
+qtyping.py:702-710).  Afterwards `Quantizer.quantize()` / `.calibrate()` reach
+the sm_100a kernels for every weight the accelerated path covers.
+
+    import ai_edge_quantizer.algorithm_manager as am
+    import aeq_b200.plugin
+    aeq_b200.plugin.install(am)
+"""
+from __future__ import annotations
+
+import functools
+
+from . import qtyping as _qt
+from .algorithms.uniform_quantize import naive_min_max_quantize
+
+# algorithm key -> (attribute of the reference module holding {op: materialize_fn},
+#                   our get_tensor_quant_params, reference module attr that owns init/calibrate)
+_BINDINGS = {
+    "min_max_uniform_quantize": ("MIN_MAX_OP_NAME_MATERIALIZE_FUNC_DICT",
+                                 naive_min_max_quantize.get_tensor_quant_params,
+                                 "naive_min_max_quantize"),
+}
+
+
+def register_binding(algorithm_key: str, dict_attr: str, get_tensor_quant_params, ref_module: str):
+  _BINDINGS[algorithm_key] = (dict_attr, get_tensor_quant_params, ref_module)
+
+
+def _adapt(fn, ref_qtyping):
+  """Wraps our function so it accepts / returns the REFERENCE's dataclasses."""
+
+  @functools.wraps(fn)
+  def get_tensor_quant_params(op_info, tensor_quant_config, tensor_content=None, tensor_qsv=None):
+    cfg = _qt.TensorQuantizationConfig(
+        num_bits=tensor_quant_config.num_bits, symmetric=tensor_quant_config.symmetric,
+        granularity=_qt.QuantGranularity(tensor_quant_config.granularity.value),
+        dtype=_qt.TensorDataType(tensor_quant_config.dtype.value),
+        algorithm_params=dict(tensor_quant_config.algorithm_params))
+    wcfg = op_info.op_quant_config.weight_tensor_config
+    ours_op = _qt.OpInfo(
+        op=op_info.op, op_name=_qt.TFLOperationName(op_info.op_name.value),
+        subgraph_op_index=op_info.subgraph_op_index,
+        op_quant_config=_qt.OpQuantizationConfig(
+            weight_tensor_config=None if wcfg is None else _qt.TensorQuantizationConfig(
+                num_bits=wcfg.num_bits, symmetric=wcfg.symmetric,
+                granularity=_qt.QuantGranularity(wcfg.granularity.value),
+                dtype=_qt.TensorDataType(wcfg.dtype.value),
+                algorithm_params=dict(wcfg.algorithm_params)),
+            skip_checks=True))
+    r = fn(ours_op, cfg, tensor_content, tensor_qsv)
+    hadamard = None
+    if r.hadamard is not None:
+      hadamard = ref_qtyping.UniformQuantParams.HadamardRotationParams(
+          random_binary_vector=r.hadamard.random_binary_vector,
+          hadamard_size=r.hadamard.hadamard_size)
+    return ref_qtyping.UniformQuantParams(
+        num_bits=r.num_bits, quantized_dimension=r.quantized_dimension, scale=r.scale,
+        zero_point=r.zero_point, symmetric=r.symmetric, quantized_data=r.quantized_data,
+        block_size=r.block_size, hadamard=hadamard,
+        custom_algorithm_param=r.custom_algorithm_param)
+
+  return get_tensor_quant_params
+
+
+def install(reference_algorithm_manager, algorithms=None) -> list[str]:
+  """Re-registers the reference's ops with device-backed arithmetic; returns the keys bound."""
+  am = reference_algorithm_manager
+  ref_qtyping = am.qtyping
+  bound = []
+  for key, (dict_attr, fn, ref_module) in _BINDINGS.items():
+    if algorithms is not None and key not in algorithms:
+      continue
+    op_dict = getattr(am, dict_attr, None) or getattr(am, "_" + dict_attr.lstrip("_"), None)
+    if op_dict is None:
+      continue
+    mod = getattr(am, ref_module)
+    adapted = _adapt(fn, ref_qtyping)
+    for op_name, materialize_func in op_dict.items():
+      inner = materialize_func.func if isinstance(materialize_func, functools.partial) else materialize_func
+      am.register_quantized_op(
+          key, op_name, mod.init_qsvs,
+          calibration_func=am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE),
+          materialize_func=functools.partial(inner, adapted),
+          update_qsv_func=am.get_update_qsv_func(key, op_name))
+    bound.append(key)
+  return bound

@@ -1,0 +1,49 @@
+"""QSV (quantisation-statistics) merge rules across calibration batches.
+
+Mirror of ai_edge_quantizer/utils/qsv_utils.py:43-122.  These are O(1)-sized
+host recurrences (a `(1,)*ndim` min/max pair per tensor per batch) that must be
+evaluated in sample order in fp32 exactly like NumPy does, so they stay NumPy
+expressions on purpose; the per-batch reductions that feed them are the device
+kernels in `aeq_b200.calibration`.  The K x K Hessian merge of GPTQ is
+device-side (`aeq_b200.device.hessian_merge`) when handed device tensors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import qtyping
+
+
+def _ema(smoothing_factor, old, new):
+  return smoothing_factor * old + (1.0 - smoothing_factor) * new
+
+
+def moving_average_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV,
+                          smoothing_factor: float = 0.95) -> qtyping.QSV:
+  """0.95 * old + 0.05 * new on min and max; first observation kept verbatim."""
+  if not qsv:
+    return new_qsv
+  return {k: _ema(smoothing_factor, qsv[k], new_qsv[k]) for k in ("min", "max")}
+
+
+def min_max_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV) -> qtyping.QSV:
+  """Union of ranges: elementwise min of mins, max of maxes."""
+  if not qsv:
+    return new_qsv
+  return {"min": np.minimum(qsv["min"], new_qsv["min"]),
+          "max": np.maximum(qsv["max"], new_qsv["max"])}
+
+
+def gptq_and_moving_average_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV) -> qtyping.QSV:
+  """EMA on min/max plus the sample-weighted running mean of the Hessian."""
+  if not qsv:
+    return new_qsv
+  out = moving_average_update(qsv, new_qsv)
+  n_old, n_new = qsv["num_samples"], new_qsv["num_samples"]
+  total = n_old + n_new
+  if total == 0:
+    out["hessian"], out["num_samples"] = new_qsv["hessian"], 0
+  else:
+    out["hessian"] = (qsv["hessian"] * n_old + new_qsv["hessian"] * n_new) / total
+    out["num_samples"] = total
+  return out

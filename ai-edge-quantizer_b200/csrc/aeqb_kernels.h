@@ -44,4 +44,25 @@ struct BlocksArgs {
 };
 cudaError_t launch_requant_blocks(BlocksArgs a, int sm_count, cudaStream_t st);
 
+// Statistics (reduce.cu).  `ws` = 8 ints of device scratch.
+cudaError_t launch_minmax_tensor(const float* x, long long n, float lo, float hi, int use_lo,
+                                 int use_hi, float* out2, int* ws, int sm_count, cudaStream_t st);
+cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn, float* mx,
+                             float* sumsq, cudaStream_t st);
+cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,
+                                cudaStream_t st);
+
+// Unfused element-wise pieces (elementwise.cu).
+cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,
+                            int bits, int symmetric, int blockwise, float* scale, int32_t* zp,
+                            uint16_t* scale_f16, cudaStream_t st);
+cudaError_t launch_quantize(const float* x, long long n, long long channels, long long inner,
+                            const float* scale, const int32_t* zp, int pstride, int bits,
+                            int symmetric, void* q, int sm_count, cudaStream_t st);
+cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long channels,
+                              long long inner, const float* scale, const int32_t* zp, int pstride,
+                              int wrap8, float* out, int sm_count, cudaStream_t st);
+cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, int sm_count,
+                        cudaStream_t st);
+
 }  // namespace aeqb

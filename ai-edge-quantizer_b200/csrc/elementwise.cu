@@ -1,0 +1,165 @@
+// Unfused building blocks with the reference's exact per-element arithmetic:
+//   scale / zero-point from min/max   (uniform_quantize_tensor.tensor_zp_scale_from_min_max, uqt:492-586)
+//   quantise with given scale / zp    (uniform_quantize, uqt:273-362)
+//   dequantise                        (uniform_dequantize, uqt:365-409)
+//   INT4 / INT2 bit packing           (transformation_utils.pack_data, transformations/transformation_utils.py:293-353)
+// The fused kernels (requant_rows.cu / requant_blocks.cu) are the hot path; these
+// cover arbitrary scale layouts (any quantised axis, GPTQ's per-column use,
+// caller-supplied parameters) and are plain grid-stride streaming kernels.
+#include "aeqb_common.cuh"
+#include "aeqb_kernels.h"
+
+namespace aeqb {
+
+namespace {
+
+// ---------------------------------------------------------------- scale / zp
+__global__ void scale_zp_kernel(const float* __restrict__ mn, const float* __restrict__ mx,
+                                const float* __restrict__ clip, long long n, int bits,
+                                int symmetric, int blockwise, float* scale, int32_t* zp,
+                                uint16_t* scale_f16) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const QRange qr = qrange(bits, symmetric != 0);
+  float c_hi = 0.f, c_lo = 0.f;
+  const bool has_clip = clip != nullptr;
+  if (has_clip) {
+    c_hi = clip[i];
+    c_lo = -c_hi;
+    if (blockwise && symmetric) {  // uqt:529-550
+      c_hi = min_nan(c_hi, 65280.0f * static_cast<float>((1 << bits) - 1));
+      c_lo = max_nan(c_lo, -65280.0f * static_cast<float>(1 << bits));
+    }
+  }
+  float s, z = 0.0f;
+  if (symmetric) {
+    float bound = max_nan(max_nan(fabsf(mn[i]), fabsf(mx[i])), 1e-9f);
+    if (has_clip) bound = min_nan(max_nan(bound, c_lo), c_hi);
+    s = __fdiv_rn(bound, qr.qmax);
+  } else {
+    const float bmax = max_nan(mx[i], 0.0f);
+    const float bmin = min_nan(mn[i], 0.0f);
+    float bound = max_nan(__fsub_rn(bmax, bmin), 1e-9f);
+    if (has_clip) bound = min_nan(max_nan(bound, -clip[i]), clip[i]);  // uqt:571-572
+    s = __fdiv_rn(bound, __fsub_rn(qr.qmax, qr.qmin));
+    z = rintf(__fsub_rn(qr.qmin, __fdiv_rn(bmin, s)));
+  }
+  uint16_t h = 0;
+  if (blockwise) s = round_scale_bf16_f16(s, &h);
+  scale[i] = s;
+  if (zp) zp[i] = rni(z);
+  if (scale_f16) scale_f16[i] = h;
+}
+
+// ---------------------------------------------------------------- quantise / dequantise
+// Tensor viewed as [outer, channels, inner]; parameter index = channel * pstride
+// (pstride 0 => one scale for everything).  Blockwise: channels = n/block,
+// inner = block, outer = 1.  int64 indices throughout.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+    quantize_kernel(const float* __restrict__ x, long long n, long long channels, long long inner,
+                    const float* __restrict__ scale, const int32_t* __restrict__ zp, int pstride,
+                    int lo, int hi, OutT* __restrict__ q) {
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += step) {
+    const long long ch = (i / inner) % channels;
+    const float s = scale[ch * pstride];
+    const float z = zp ? static_cast<float>(zp[ch * pstride]) : 0.0f;
+    const float t = __fadd_rn(__fdiv_rn(x[i], s), z);
+    q[i] = static_cast<OutT>(clampi(rni(t), lo, hi));
+  }
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(256)
+    dequantize_kernel(const InT* __restrict__ q, long long n, long long channels, long long inner,
+                      const float* __restrict__ scale, const int32_t* __restrict__ zp, int pstride,
+                      int wrap8, float* __restrict__ out) {
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += step) {
+    const long long ch = (i / inner) % channels;
+    const int z = zp ? zp[ch * pstride] : 0;
+    // NumPy evaluates `q - zp` in the operands' common integer type: int8 - int8
+    // wraps modulo 256 (wrap8); wider types are exact.  One fp32 multiply follows.
+    int d = static_cast<int>(q[i]) - z;
+    if (wrap8) d = static_cast<int>(static_cast<int8_t>(d));
+    out[i] = __fmul_rn(static_cast<float>(d), scale[ch * pstride]);
+  }
+}
+
+// ---------------------------------------------------------------- bit packing
+__global__ void __launch_bounds__(256)
+    pack_kernel(const int8_t* __restrict__ q, long long n, int bits, uint8_t* __restrict__ out,
+                long long n_out) {
+  const int per = 8 / bits;
+  const unsigned mask = (1u << bits) - 1u;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n_out; j += step) {
+    unsigned b = 0;
+    for (int k = 0; k < per; ++k) {
+      const long long e = j * per + k;
+      if (e < n) b |= (static_cast<unsigned>(q[e]) & mask) << (bits * k);  // zero-padded tail
+    }
+    out[j] = static_cast<uint8_t>(b);
+  }
+}
+
+unsigned grid_for(long long n, int sm_count) {
+  long long g = (n + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,
+                            int bits, int symmetric, int blockwise, float* scale, int32_t* zp,
+                            uint16_t* scale_f16, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  scale_zp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      mn, mx, clip, n, bits, symmetric, blockwise, scale, zp, scale_f16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantize(const float* x, long long n, long long channels, long long inner,
+                            const float* scale, const int32_t* zp, int pstride, int bits,
+                            int symmetric, void* q, int sm_count, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const QRange qr = qrange(bits, symmetric != 0);
+  const unsigned g = grid_for(n, sm_count);
+  if (bits <= 8)
+    quantize_kernel<int8_t><<<g, 256, 0, st>>>(x, n, channels, inner, scale, zp, pstride, qr.lo, qr.hi, static_cast<int8_t*>(q));
+  else if (bits <= 16)
+    quantize_kernel<int16_t><<<g, 256, 0, st>>>(x, n, channels, inner, scale, zp, pstride, qr.lo, qr.hi, static_cast<int16_t*>(q));
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long channels,
+                              long long inner, const float* scale, const int32_t* zp, int pstride,
+                              int wrap8, float* out, int sm_count, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned g = grid_for(n, sm_count);
+  if (q_bytes == 1)
+    dequantize_kernel<int8_t><<<g, 256, 0, st>>>(static_cast<const int8_t*>(q), n, channels, inner, scale, zp, pstride, wrap8, out);
+  else if (q_bytes == 2)
+    dequantize_kernel<int16_t><<<g, 256, 0, st>>>(static_cast<const int16_t*>(q), n, channels, inner, scale, zp, pstride, wrap8, out);
+  else if (q_bytes == 4)
+    dequantize_kernel<int32_t><<<g, 256, 0, st>>>(static_cast<const int32_t*>(q), n, channels, inner, scale, zp, pstride, wrap8, out);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, int sm_count,
+                        cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long n_out = (n * bits + 7) / 8;
+  pack_kernel<<<grid_for(n_out, sm_count), 256, 0, st>>>(q, n, bits, out, n_out);
+  return cudaGetLastError();
+}
+
+}  // namespace aeqb

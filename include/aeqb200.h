@@ -78,6 +78,59 @@ AEQB_API int aeqb_requant_blocks_f32(const float* x, int64_t rows, int64_t cols,
                             const float* clip, int8_t* q, uint8_t* packed, float* scale,
                             uint16_t* scale_f16, void* stream);
 
+/* ---------------------------------------------------------------- statistics
+ * Whole-tensor min/max with the open-interval validity filter and raw fallback:
+ * out2[0] = min{x : x > lo} (raw NaN-propagating min when nothing passes or
+ * use_lo == 0), out2[1] = max{x : x < hi} likewise.  Replaces
+ * common_quantize.get_activation_min_max (common_quantize.py:1362-1413), the
+ * reduction inside naive_min_max_quantize.min_max_calibrate (:181-226) and
+ * gptq.calibrate's min/max (gptq.py:84-98).  ws: aeqb_minmax_workspace_bytes()
+ * bytes of device scratch. */
+AEQB_API size_t aeqb_minmax_workspace_bytes(void);
+AEQB_API int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int use_lo,
+                                    int use_hi, float* out2, void* ws, void* stream);
+
+/* Per-row min, max and sum of squares of a [rows, cols] matrix (any may be
+ * NULL).  min/max: common_quantize.init_tensor_min_max CHANNELWISE branch
+ * (common_quantize.py:1337-1344); sumsq: the reduction of mse.get_tensor_quant_params
+ * (algorithms/uniform_quantize/mse.py:100-107). */
+AEQB_API int aeqb_row_stats_f32(const float* x, int64_t rows, int64_t cols, float* mn, float* mx,
+                                float* sumsq, void* stream);
+
+/* Per-block min and max, shape [rows, cols/block] (common_quantize.py:1345-1358). */
+AEQB_API int aeqb_minmax_blocks_f32(const float* x, int64_t rows, int64_t cols, int block,
+                                    float* mn, float* mx, void* stream);
+
+/* ---------------------------------------------------------------- unfused pieces
+ * tensor_zp_scale_from_min_max (uqt:492-586) on n (min, max[, clip]) triples.
+ * blockwise != 0 applies the bf16->fp16 scale rounding (uqt:577-581) and, with
+ * clip, the fp16 range limit (uqt:529-550).  zp / scale_f16 may be NULL. */
+AEQB_API int aeqb_scale_zp_from_minmax(const float* mn, const float* mx, const float* clip,
+                                       int64_t n, int bits, int symmetric, int blockwise,
+                                       float* scale, int32_t* zp, uint16_t* scale_f16,
+                                       void* stream);
+
+/* uniform_quantize (uqt:273-362) with caller-supplied parameters.  The tensor is
+ * viewed as [outer, channels, inner] (n = outer*channels*inner); element i uses
+ * parameter ((i / inner) % channels) * param_stride (param_stride 0: one scale
+ * for the whole tensor; blockwise: channels = n/block, inner = block).
+ * bits <= 8 writes int8, bits <= 16 writes int16.  zp may be NULL (zeros). */
+AEQB_API int aeqb_quantize_f32(const float* x, int64_t n, int64_t channels, int64_t inner,
+                               const float* scale, const int32_t* zp, int param_stride, int bits,
+                               int symmetric, void* q, void* stream);
+
+/* uniform_dequantize (uqt:365-409): out = (q - zp) * scale in fp32.  q_bytes is
+ * 1, 2 or 4 (int8/int16/int32).  wrap8 != 0 reproduces NumPy's int8 - int8
+ * wrap-around of the difference. */
+AEQB_API int aeqb_dequantize_f32(const void* q, int q_bytes, int64_t n, int64_t channels,
+                                 int64_t inner, const float* scale, const int32_t* zp,
+                                 int param_stride, int wrap8, float* out, void* stream);
+
+/* transformation_utils.pack_data (transformations/transformation_utils.py:293-353):
+ * INT4 two nibbles per byte (even index low), INT2 four crumbs per byte (index 0
+ * lowest), odd tail zero padded.  out: ceil(n*bits/8) bytes.  bits 2 or 4. */
+AEQB_API int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,13 +374,26 @@ def gptq_hessian(x):
   return (2.0 / n) * x2.T.dot(x2)
 
 
-def gptq_hessian_inverse(h, damp: float = 0.01):
-  """Damped inverse through Cholesky + triangular inverse (gptq.py:111-128)."""
-  import scipy.linalg
-  h = np.array(h, copy=True)
+def gptq_damped_diagonal(h, damp: float = 0.01):
+  """diag with zeros -> 1, plus damp * mean (gptq.py:115-117)."""
   d = np.diag(h)
   d = np.where(d, d, 1.0)
-  d = d + damp * np.mean(d)
+  return d + damp * np.mean(d)
+
+
+def gptq_hessian_inverse(h, damp: float = 0.01, mutate: bool = False):
+  """Damped inverse through Cholesky + triangular inverse (gptq.py:111-128).
+
+  Reference quirk: `orig_diag = np.diag(hessian)` is a view, so the "restore"
+  at gptq.py:123 writes the damped diagonal back onto itself and the CALLER's
+  Hessian keeps the damping (it accumulates when one activation feeds several
+  FC ops).  `mutate=True` reproduces that side effect on `h`.
+  """
+  import scipy.linalg
+  d = gptq_damped_diagonal(h, damp)
+  if mutate:
+    np.fill_diagonal(h, d)
+  h = np.array(h, copy=True)
   np.fill_diagonal(h, d)
   low = np.linalg.cholesky(h)
   low_inv, info = scipy.linalg.lapack.strtri(low, lower=True)
