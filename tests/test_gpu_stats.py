@@ -131,4 +131,4 @@ def test_scale_zp_kernel_matches_oracle(cuda):
           with np.errstate(all="ignore"):
             ozp, osc = O.scale_zp(mn, mx, bits, sym, blockwise, c)
           np.testing.assert_array_equal(sc.cpu().numpy(), osc)
-          np.testing.assert_array_equal(zp.cpu().numpy(), ozp.astype(np.int32))
+          np.testing.assert_array_equal(zp.cpu().numpy().astype(ozp.dtype), ozp)  # uqt:585 cast wraps
