@@ -31,6 +31,8 @@ SIGNATURES = {
     "aeqb_requant_given_minmax_f32":
         (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "aeqb_requant_blocks_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aeqb_requant_rows_batch_f32": (_I, [_P, _L, _I, _I, _P]),
+    "aeqb_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I, _P]),
     "aeqb_minmax_workspace_bytes": (_c.c_size_t, []),
     "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),
     "aeqb_row_stats_f32": (_I, [_P, _L, _L, _P, _P, _P, _P]),
@@ -40,6 +42,18 @@ SIGNATURES = {
     "aeqb_dequantize_f32": (_I, [_P, _I, _L, _L, _L, _P, _P, _I, _I, _P, _P]),
     "aeqb_pack_bits": (_I, [_P, _L, _I, _P, _P]),
 }
+
+
+class RowsJob(_c.Structure):
+  """aeqb_rows_job (include/aeqb200.h)."""
+  _fields_ = [("x", _P), ("rows", _L), ("cols", _L), ("clip", _P), ("q", _P),
+              ("packed", _P), ("scale", _P), ("zp", _P)]
+
+
+class BlocksJob(_c.Structure):
+  """aeqb_blocks_job (include/aeqb200.h)."""
+  _fields_ = [("x", _P), ("rows", _L), ("cols", _L), ("clip", _P), ("q", _P),
+              ("packed", _P), ("scale", _P), ("scale_f16", _P)]
 
 
 class AeqbError(RuntimeError):

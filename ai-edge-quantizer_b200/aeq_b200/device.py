@@ -219,3 +219,65 @@ def pack_bits(q: torch.Tensor, bits: int) -> torch.Tensor:
   out = torch.empty((n * bits + 7) // 8, dtype=torch.uint8, device=q.device)
   _lib.call("aeqb_pack_bits", _ptr(q), n, bits, _ptr(out), _stream())
   return out
+
+
+# ------------------------------------------------------------------ batched (whole model)
+def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = True,
+                       want_packed: bool = False, outs=None):
+  """Per-channel requantisation of many tensors in as few persistent launches as possible.
+
+  Returns a list of Requantized.  `outs` may carry preallocated outputs from a previous call
+  (same shapes) to keep the loop allocation-free.
+  """
+  import ctypes
+  n = len(xs)
+  if outs is None:
+    outs = []
+    for x in xs:
+      _check_f32_2d(x)
+      rows, cols = x.shape
+      dev = x.device
+      outs.append(Requantized(
+          torch.empty((rows, cols), dtype=torch.int8, device=dev) if want_q else None,
+          torch.empty(rows * cols * bits // 8, dtype=torch.uint8, device=dev) if want_packed else None,
+          torch.empty((rows, 1), dtype=torch.float32, device=dev),
+          torch.empty((rows, 1), dtype=torch.int32, device=dev)))
+  jobs = (_lib.RowsJob * n)()
+  for i, (x, o) in enumerate(zip(xs, outs)):
+    jobs[i] = _lib.RowsJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
+                           _ptr(o.scale), _ptr(o.zero_point))
+  _lib.call("aeqb_requant_rows_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), n, bits,
+            int(symmetric), _stream())
+  return outs
+
+
+def requant_blocks_batch(xs, block: int, bits: int, want_q: bool = False,
+                         want_packed: bool = True, want_scale: bool = False,
+                         want_scale_f16: bool = True, outs=None):
+  """Blockwise requantisation of many tensors in as few persistent launches as possible."""
+  import ctypes
+  n = len(xs)
+  if outs is None:
+    outs = []
+    for x in xs:
+      _check_f32_2d(x)
+      rows, cols = x.shape
+      if cols % block:
+        raise ValueError(
+            f"Quantized dimension {cols} in tensor shape {tuple(x.shape)} is not"
+            f" divisible by block size {block}.")
+      dev = x.device
+      nb = cols // block
+      outs.append(Requantized(
+          torch.empty((rows, cols), dtype=torch.int8, device=dev) if want_q else None,
+          torch.empty(rows * cols // 2, dtype=torch.uint8, device=dev) if want_packed else None,
+          torch.empty((rows, nb), dtype=torch.float32, device=dev) if want_scale else None,
+          None,
+          torch.empty((rows, nb), dtype=torch.float16, device=dev) if want_scale_f16 else None))
+  jobs = (_lib.BlocksJob * n)()
+  for i, (x, o) in enumerate(zip(xs, outs)):
+    jobs[i] = _lib.BlocksJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
+                             _ptr(o.scale), _ptr(o.scale_f16))
+  _lib.call("aeqb_requant_blocks_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), n, block, bits,
+            _stream())
+  return outs

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/aeqb200.h"
 #include "aeqb_kernels.h"
 
@@ -45,41 +47,87 @@ extern "C" {
 int aeqb_version(void) { return AEQB_VERSION; }
 const char* aeqb_last_error(void) { return g_err; }
 
-int aeqb_requant_rows_f32(const float* x, int64_t rows, int64_t cols, int bits, int symmetric,
-                          const float* clip, int8_t* q, uint8_t* packed, float* scale,
-                          int32_t* zp, void* stream) {
+// ---- shared batching logic --------------------------------------------------
+namespace {
+
+struct RowsOpts { int bits, symmetric; };
+
+// Runs every job: stream-class jobs are grouped into <= kMaxInlineJobs batches per
+// class (one persistent launch each), the rest go through the generic kernel.
+int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who) {
+  const int sms = sm_count();
+  for (int klass = 1; klass <= 2; ++klass) {
+    aeqb::RowsBatch b{};
+    b.bits = o.bits; b.symmetric = o.symmetric;
+    auto flush = [&]() -> int {
+      if (b.n_jobs == 0) return 0;
+      int rc = check(aeqb::launch_requant_rows_stream(b, klass, sms, st), who);
+      b.n_jobs = 0; b.n_tiles = 0;
+      return rc;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+      aeqb::RowsJob j = jobs[i];
+      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != klass) continue;
+      j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
+      j.tile0 = b.n_tiles;
+      j.tile_end = j.tile0 + (j.rows + j.rows_per_tile - 1) / j.rows_per_tile;
+      b.n_tiles = j.tile_end;
+      b.jobs[b.n_jobs++] = j;
+      if (b.n_jobs == aeqb::kMaxInlineJobs) { if (int rc = flush()) return rc; }
+    }
+    if (int rc = flush()) return rc;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const aeqb::RowsJob& j = jobs[i];
+    if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != 0) continue;
+    if (j.packed && (j.cols % (8 / o.bits) != 0))
+      return fail("%s: packed output of a [%lld, %d] tensor would straddle rows; pack separately",
+                  who, (long long)j.rows, j.cols);
+    if (int rc = check(aeqb::launch_requant_rows_generic(j, o.bits, o.symmetric, st), who)) return rc;
+  }
+  return 0;
+}
+
+int run_blocks(const aeqb::BlocksJob* jobs, int64_t n, int block, int bits, cudaStream_t st,
+               const char* who) {
+  const int sms = sm_count();
+  aeqb::BlocksBatch b{};
+  b.block = block; b.bits = bits;
+  bool bq = false, bp = false;
+  auto flush = [&]() -> int {
+    if (b.n_jobs == 0) return 0;
+    int rc = check(aeqb::launch_requant_blocks_stream(b, bq, bp, sms, st), who);
+    b.n_jobs = 0; b.n_tiles = 0;
+    return rc;
+  };
+  for (int64_t i = 0; i < n; ++i) {
+    aeqb::BlocksJob j = jobs[i];
+    if (j.n <= 0) continue;
+    if (!aeqb::blocks_job_streamable(j)) {
+      if (int rc = check(aeqb::launch_requant_blocks_generic(j, block, bits, st), who)) return rc;
+      continue;
+    }
+    const bool jq = j.q != nullptr, jp = j.packed != nullptr;
+    if (b.n_jobs && (jq != bq || jp != bp)) { if (int rc = flush()) return rc; }
+    bq = jq; bp = jp;
+    j.tile0 = b.n_tiles;
+    j.tile_end = j.tile0 + aeqb::blocks_job_tiles(j.n);
+    b.n_tiles = j.tile_end;
+    b.jobs[b.n_jobs++] = j;
+    if (b.n_jobs == aeqb::kMaxInlineJobs) { if (int rc = flush()) return rc; }
+  }
+  return flush();
+}
+
+int rows_args_ok(int64_t rows, int64_t cols, int bits, const void* packed, const void* x) {
   if (rows < 0 || cols < 0 || cols > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
   if (!bits_ok(bits)) return fail("unsupported num_bits %d (2, 4 or 8)", bits);
   if (packed && bits == 8) return fail("packed output needs num_bits 2 or 4");
   if (rows * cols > 0 && !x) return fail("x is NULL");
-  aeqb::RowsArgs a{};
-  a.x = x; a.q = q; a.packed = packed; a.scale = scale; a.zp = zp; a.clip = clip;
-  a.rows = rows; a.cols = static_cast<int>(cols); a.bits = bits; a.symmetric = symmetric ? 1 : 0;
-  a.mm_stride = 1; a.clip_stride = 1; a.out_stride = 1;
-  return check(aeqb::launch_requant_rows(a, sm_count(), static_cast<cudaStream_t>(stream)),
-               "aeqb_requant_rows_f32");
+  return 0;
 }
 
-int aeqb_requant_given_minmax_f32(const float* x, int64_t rows, int64_t cols, int bits,
-                                  int symmetric, const float* mn, const float* mx,
-                                  const float* clip, int per_row, int8_t* q, uint8_t* packed,
-                                  float* scale, int32_t* zp, void* stream) {
-  if (rows < 0 || cols < 0 || cols > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
-  if (!bits_ok(bits)) return fail("unsupported num_bits %d (2, 4 or 8)", bits);
-  if (packed && bits == 8) return fail("packed output needs num_bits 2 or 4");
-  if (!mn || !mx) return fail("min / max are NULL");
-  aeqb::RowsArgs a{};
-  a.x = x; a.q = q; a.packed = packed; a.scale = scale; a.zp = zp; a.clip = clip;
-  a.given_min = mn; a.given_max = mx;
-  a.rows = rows; a.cols = static_cast<int>(cols); a.bits = bits; a.symmetric = symmetric ? 1 : 0;
-  a.mm_stride = a.clip_stride = a.out_stride = per_row ? 1 : 0;
-  return check(aeqb::launch_requant_rows(a, sm_count(), static_cast<cudaStream_t>(stream)),
-               "aeqb_requant_given_minmax_f32");
-}
-
-int aeqb_requant_blocks_f32(const float* x, int64_t rows, int64_t cols, int block, int bits,
-                            const float* clip, int8_t* q, uint8_t* packed, float* scale,
-                            uint16_t* scale_f16, void* stream) {
+int blocks_args_ok(int64_t rows, int64_t cols, int block, int bits, const void* packed, const void* x) {
   if (rows < 0 || cols < 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
   if (block != 32 && block != 64 && block != 128 && block != 256) return fail("unsupported block size %d", block);
   if (cols % block)
@@ -87,11 +135,79 @@ int aeqb_requant_blocks_f32(const float* x, int64_t rows, int64_t cols, int bloc
   if (!bits_ok(bits)) return fail("unsupported num_bits %d (2, 4 or 8)", bits);
   if (packed && bits != 4) return fail("fused packed output needs num_bits 4");
   if (rows * cols > 0 && !x) return fail("x is NULL");
-  aeqb::BlocksArgs a{};
-  a.x = x; a.q = q; a.packed = packed; a.scale = scale; a.scale_f16 = scale_f16; a.clip = clip;
-  a.n = rows * cols; a.block = block; a.bits = bits;
-  return check(aeqb::launch_requant_blocks(a, sm_count(), static_cast<cudaStream_t>(stream)),
-               "aeqb_requant_blocks_f32");
+  return 0;
+}
+
+}  // namespace
+
+int aeqb_requant_rows_f32(const float* x, int64_t rows, int64_t cols, int bits, int symmetric,
+                          const float* clip, int8_t* q, uint8_t* packed, float* scale,
+                          int32_t* zp, void* stream) {
+  if (int rc = rows_args_ok(rows, cols, bits, packed, x)) return rc;
+  aeqb::RowsJob j{};
+  j.x = x; j.q = q; j.packed = packed; j.scale = scale; j.zp = zp; j.clip = clip;
+  j.rows = rows; j.cols = static_cast<int>(cols);
+  j.mm_stride = 1; j.clip_stride = 1; j.out_stride = 1;
+  return run_rows(&j, 1, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
+                  "aeqb_requant_rows_f32");
+}
+
+int aeqb_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits, int symmetric,
+                                void* stream) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad job list");
+  std::vector<aeqb::RowsJob> v(static_cast<size_t>(n_jobs));
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const aeqb_rows_job& a = jobs[i];
+    if (int rc = rows_args_ok(a.rows, a.cols, bits, a.packed, a.x)) return rc;
+    aeqb::RowsJob j{};
+    j.x = a.x; j.q = a.q; j.packed = a.packed; j.scale = a.scale; j.zp = a.zp; j.clip = a.clip;
+    j.rows = a.rows; j.cols = static_cast<int>(a.cols);
+    j.mm_stride = 1; j.clip_stride = 1; j.out_stride = 1;
+    v[static_cast<size_t>(i)] = j;
+  }
+  return run_rows(v.data(), n_jobs, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
+                  "aeqb_requant_rows_batch_f32");
+}
+
+int aeqb_requant_given_minmax_f32(const float* x, int64_t rows, int64_t cols, int bits,
+                                  int symmetric, const float* mn, const float* mx,
+                                  const float* clip, int per_row, int8_t* q, uint8_t* packed,
+                                  float* scale, int32_t* zp, void* stream) {
+  if (int rc = rows_args_ok(rows, cols, bits, packed, x)) return rc;
+  if (!mn || !mx) return fail("min / max are NULL");
+  aeqb::RowsJob j{};
+  j.x = x; j.q = q; j.packed = packed; j.scale = scale; j.zp = zp; j.clip = clip;
+  j.given_min = mn; j.given_max = mx;
+  j.rows = rows; j.cols = static_cast<int>(cols);
+  j.mm_stride = j.clip_stride = j.out_stride = per_row ? 1 : 0;
+  return run_rows(&j, 1, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
+                  "aeqb_requant_given_minmax_f32");
+}
+
+int aeqb_requant_blocks_f32(const float* x, int64_t rows, int64_t cols, int block, int bits,
+                            const float* clip, int8_t* q, uint8_t* packed, float* scale,
+                            uint16_t* scale_f16, void* stream) {
+  if (int rc = blocks_args_ok(rows, cols, block, bits, packed, x)) return rc;
+  aeqb::BlocksJob j{};
+  j.x = x; j.q = q; j.packed = packed; j.scale = scale; j.scale_f16 = scale_f16; j.clip = clip;
+  j.n = rows * cols;
+  return run_blocks(&j, 1, block, bits, static_cast<cudaStream_t>(stream), "aeqb_requant_blocks_f32");
+}
+
+int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block, int bits,
+                                  void* stream) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad job list");
+  std::vector<aeqb::BlocksJob> v(static_cast<size_t>(n_jobs));
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const aeqb_blocks_job& a = jobs[i];
+    if (int rc = blocks_args_ok(a.rows, a.cols, block, bits, a.packed, a.x)) return rc;
+    aeqb::BlocksJob j{};
+    j.x = a.x; j.q = a.q; j.packed = a.packed; j.scale = a.scale; j.scale_f16 = a.scale_f16;
+    j.clip = a.clip; j.n = a.rows * a.cols;
+    v[static_cast<size_t>(i)] = j;
+  }
+  return run_blocks(v.data(), n_jobs, block, bits, static_cast<cudaStream_t>(stream),
+                    "aeqb_requant_blocks_batch_f32");
 }
 
 size_t aeqb_minmax_workspace_bytes(void) { return 8 * sizeof(int); }

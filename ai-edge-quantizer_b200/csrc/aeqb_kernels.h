@@ -6,8 +6,12 @@
 
 namespace aeqb {
 
-// Per-channel / per-tensor fused requantisation of a [rows, cols] fp32 matrix.
-struct RowsArgs {
+constexpr int kMaxInlineJobs = 64;
+
+// Per-channel / per-tensor fused requantisation of [rows, cols] fp32 matrices.
+// Up to kMaxInlineJobs tensors travel by value in the kernel parameters, so a
+// batch needs no device-side table, no workspace and no extra copy.
+struct RowsJob {
   const float* x;
   int8_t* q;        // [rows*cols] one value per byte, or null
   uint8_t* packed;  // [rows*cols*bits/8] INT4 / INT2 packed, or null
@@ -18,31 +22,51 @@ struct RowsArgs {
   const float* given_max;
   long long rows;
   int cols;
+  int rows_per_tile;            // launcher
+  int mm_stride, clip_stride;   // 0: one value for the whole tensor, 1: per row
+  int out_stride;
+  long long tile0, tile_end;    // this job's tile range inside the batch (launcher)
+};
+struct RowsBatch {
+  RowsJob jobs[kMaxInlineJobs];
+  int n_jobs;
   int bits;
   int symmetric;
-  int mm_stride;    // 0: one min/max for the whole tensor, 1: per row
-  int clip_stride;  // 0 / 1
-  int out_stride;   // 0 / 1
-  int rows_per_tile;  // filled by the launcher
-  long long n_tiles;  // filled by the launcher
+  long long n_tiles;
 };
-cudaError_t launch_requant_rows(RowsArgs a, int sm_count, cudaStream_t st);
+// 0: generic kernel, 1: 32 KiB stages (rows <= 8192 floats), 2: 64 KiB stages.
+int rows_job_class(const RowsJob& j, int bits);
+int rows_job_rows_per_tile(const RowsJob& j, int klass);
+cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count, cudaStream_t st);
+cudaError_t launch_requant_rows_generic(const RowsJob& j, int bits, int symmetric, cudaStream_t st);
 
-// Blockwise symmetric requantisation of a flat fp32 array cut into `block`-long
-// groups (blocks never straddle rows because cols % block == 0).
-struct BlocksArgs {
+// Blockwise symmetric requantisation: each job is a flat fp32 array cut into
+// `block`-long groups (blocks never straddle rows because cols % block == 0).
+// Up to kMaxInlineJobs tensors travel by value in the kernel parameters, so a
+// batch needs no device-side table, no workspace and no extra copy.
+struct BlocksJob {
   const float* x;
   int8_t* q;            // [n] or null
-  uint8_t* packed;      // [n*bits/8] or null (bits 4 only)
+  uint8_t* packed;      // [n/2] or null (bits 4 only)
   float* scale;         // [n/block] fp32 (already bf16->fp16 rounded), or null
   uint16_t* scale_f16;  // [n/block] fp16 bit patterns, or null
   const float* clip;    // optional [n/block]
   long long n;
+  long long tile0, tile_end;  // this job's tile range inside the batch (launcher)
+};
+struct BlocksBatch {
+  BlocksJob jobs[kMaxInlineJobs];
+  int n_jobs;
   int block;
   int bits;
-  long long n_tiles;  // filled by the launcher
+  long long n_tiles;
 };
-cudaError_t launch_requant_blocks(BlocksArgs a, int sm_count, cudaStream_t st);
+long long blocks_job_tiles(long long n);
+bool blocks_job_streamable(const BlocksJob& j);
+cudaError_t launch_requant_blocks_stream(const BlocksBatch& b, bool out_q, bool out_p,
+                                         int sm_count, cudaStream_t st);
+cudaError_t launch_requant_blocks_generic(const BlocksJob& j, int block, int bits,
+                                          cudaStream_t st);
 
 // Statistics (reduce.cu).  `ws` = 8 ints of device scratch.
 cudaError_t launch_minmax_tensor(const float* x, long long n, float lo, float hi, int use_lo,

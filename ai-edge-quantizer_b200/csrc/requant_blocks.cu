@@ -11,12 +11,20 @@
 //   quantize_tensor._perform_blockwise_quantization fp16 scale (:129-133)
 // HBM traffic: 4 B read + 0.5 B packed + 2/block B fp16 scale per weight.
 //
-// Because cols % block == 0, the [rows, cols] matrix is a flat stream of
-// blocks and the scale tensor [rows, cols/block] is that stream's block index.
-// Tile-stream as in requant_rows.cu; here every lane owns 8 consecutive floats
-// (two float4, loaded in a swizzled order so that LDS.128 is bank-conflict
-// free), block/8 lanes share a block, and the block never leaves registers:
-// shared memory is read once.
+// Because cols % block == 0, a [rows, cols] matrix is a flat stream of blocks and
+// its scale tensor [rows, cols/block] is that stream's block index; a batch of
+// tensors is the concatenation of their streams (one persistent launch for a
+// whole model's weight buffers).  Tile-stream: one producer lane keeps a 3-stage
+// shared-memory ring full with 1-D TMA bulk copies; every consumer lane owns 8
+// consecutive floats (two float4, loaded in a swizzled order so LDS.128 is
+// bank-conflict free), block/8 lanes share a block, and the data never leaves
+// registers between the |x| max and the quantise step: shared memory is read once.
+//
+// Fast path (no clipping constants, fp16-normal scale): x/scale via the hoisted
+// exact divide (3 FFMA), rint via one magic-number FADD, nibbles assembled by
+// IMAD Horner steps + one PRMT; the clip to [qmin, qmax] provably never binds
+// (|x|/scale <= qmax / (1 - 2^-9) < qmax + 0.5).  Anything else (clip given,
+// scale flushed to 0 / subnormal / inf / NaN) takes the IEEE-divide path.
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
@@ -30,30 +38,25 @@ constexpr int kStageFloats = kStageBytes / 4;
 constexpr int kNW = 8;
 constexpr int kSlice = 256;  // floats handled by one warp iteration
 
-struct BlockQ {
-  DivBy div;
-  float scale;
-  uint16_t f16;
+struct StageDesc {
+  BlocksJob job;
+  long long e0;  // first element of the tile inside job.x
+  int ne;        // elements in the tile
 };
 
-// uqt:552-563 + :577-581 for one block.
-__device__ __forceinline__ BlockQ finalize_block(const BlocksArgs& a, long long blk, float amax) {
-  const QRange qr = qrange(a.bits, true);
+// uqt:552-563 + :577-581 for one block (clip / degenerate path).
+__device__ __forceinline__ float block_scale_slow(float amax, const float* clip, long long blk,
+                                                  int bits, float qmax, uint16_t* f16) {
   float bound = max_nan(amax, 1e-9f);
-  if (a.clip) {
-    // uqt:529-550: with clipping values the bound is also kept inside what an
-    // fp16 scale can represent.
-    const float c = a.clip[blk];
-    const float f16_hi = 65280.0f * static_cast<float>((1 << a.bits) - 1);
-    const float f16_lo = -65280.0f * static_cast<float>(1 << a.bits);
-    const float hi = min_nan(c, f16_hi);
-    const float lo = max_nan(-c, f16_lo);
+  if (clip) {
+    // uqt:529-550: with clipping values the bound also stays inside what an fp16
+    // scale can represent.
+    const float c = clip[blk];
+    const float hi = min_nan(c, 65280.0f * static_cast<float>((1 << bits) - 1));
+    const float lo = max_nan(-c, -65280.0f * static_cast<float>(1 << bits));
     bound = min_nan(max_nan(bound, lo), hi);
   }
-  BlockQ r;
-  r.scale = round_scale_bf16_f16(__fdiv_rn(bound, qr.qmax), &r.f16);
-  r.div = make_div(r.scale, amax);
-  return r;
+  return round_scale_bf16_f16(__fdiv_rn(bound, qmax), f16);
 }
 
 template <int LPB>  // lanes per block = block / 8
@@ -63,18 +66,19 @@ __device__ __forceinline__ float group_max_nan(float v) {
   return v;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__((kNW + 1) * 32)
-    requant_blocks_stream(const __grid_constant__ BlocksArgs a) {
+template <int BLOCK, bool OUT_Q, bool OUT_P>
+__global__ void __launch_bounds__((kNW + 1) * 32, 2)
+    requant_blocks_stream(const __grid_constant__ BlocksBatch b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ StageDesc desc[kStages];
   constexpr int LPB = BLOCK / 8;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const long long n_tiles = a.n_tiles;
+  const long long n_tiles = b.n_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -87,34 +91,52 @@ __global__ void __launch_bounds__((kNW + 1) * 32)
 
   if (warp == kNW) {  // ---------------- producer
     if (lane == 0) {
+      int j = 0;
+      BlocksJob job = b.jobs[0];
       long long it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = static_cast<int>(it % kStages);
         const long long round = it / kStages;
         if (round > 0) mbar_wait(&empty_bar[s], static_cast<uint32_t>((round - 1) & 1));
-        const long long e0 = tile * kStageFloats;
-        const long long ne = min(static_cast<long long>(kStageFloats), a.n - e0);
+        while (tile >= job.tile_end) job = b.jobs[++j];
+        const long long e0 = (tile - job.tile0) * kStageFloats;
+        const long long ne = min(static_cast<long long>(kStageFloats), job.n - e0);
+        desc[s].job = job;
+        desc[s].e0 = e0;
+        desc[s].ne = static_cast<int>(ne);
         const uint32_t bytes = static_cast<uint32_t>(ne * 4);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(smem_raw + static_cast<size_t>(s) * kStageBytes, a.x + e0, bytes, &full_bar[s]);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);  // release: desc is visible to waiters
+        bulk_g2s(smem_raw + static_cast<size_t>(s) * kStageBytes, job.x + e0, bytes, &full_bar[s]);
       }
     }
     return;
   }
 
   // ---------------- consumers
-  const QRange qr = qrange(a.bits, true);
-  const int sw = (lane >> 2) & 1;  // load-order swizzle
+  const QRange qr = qrange(b.bits, true);
+  const DivBy dq = make_recip(qr.qmax);  // bound / qmax with a hoisted reciprocal
+  const int sw = (lane >> 2) & 1;            // load-order swizzle
+  const uint32_t sel = sw ? 0x1054u : 0x5410u;  // PRMT: which float4 holds the low elements
+  const bool leader = (lane & (LPB - 1)) == 0;
   long long it = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int s = static_cast<int>(it % kStages);
     const uint32_t ph = static_cast<uint32_t>((it / kStages) & 1);
-    const long long e0 = tile * kStageFloats;
-    const int ne = static_cast<int>(min(static_cast<long long>(kStageFloats), a.n - e0));
-    const int nslices = (ne + kSlice - 1) / kSlice;
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * kStageBytes);
 
     mbar_wait(&full_bar[s], ph);
+
+    const long long e0 = desc[s].e0;
+    const int ne = desc[s].ne;
+    const float* clip = desc[s].job.clip;
+    int8_t* qp = OUT_Q ? desc[s].job.q + e0 : nullptr;
+    uint8_t* pp = OUT_P ? desc[s].job.packed + (e0 >> 1) : nullptr;
+    float* sp = desc[s].job.scale;
+    uint16_t* hp = desc[s].job.scale_f16;
+    const long long blk0 = e0 / BLOCK;
+    const bool w_scale = leader && sp != nullptr;
+    const bool w_f16 = leader && hp != nullptr;
+    const int nslices = (ne + kSlice - 1) / kSlice;
 
     for (int sl = warp; sl < nslices; sl += kNW) {
       const int f0 = sl * kSlice + lane * 8;  // first float of this lane inside the tile
@@ -124,48 +146,57 @@ __global__ void __launch_bounds__((kNW + 1) * 32)
         va = t4[(f0 >> 2) + sw];        // sw == 0: elements 0..3, else 4..7
         vb = t4[(f0 >> 2) + (sw ^ 1)];
       }
-      float amax = absmax4(absmax4(0.0f, va), vb);
-      amax = group_max_nan<LPB>(amax);
-      const long long blk = (e0 + f0) / BLOCK;
-      BlockQ bq;
-      if (valid) bq = finalize_block(a, blk, amax);
+      const float amax = group_max_nan<LPB>(absmax4(absmax4(0.0f, va), vb));
       if (!valid) continue;
+      const int blk = f0 / BLOCK;
 
-      int qa[4], qb[4];
-      if (bq.div.fast) {
-        qa[0] = clampi(rni(div_fast(va.x, bq.div)), qr.lo, qr.hi);
-        qa[1] = clampi(rni(div_fast(va.y, bq.div)), qr.lo, qr.hi);
-        qa[2] = clampi(rni(div_fast(va.z, bq.div)), qr.lo, qr.hi);
-        qa[3] = clampi(rni(div_fast(va.w, bq.div)), qr.lo, qr.hi);
-        qb[0] = clampi(rni(div_fast(vb.x, bq.div)), qr.lo, qr.hi);
-        qb[1] = clampi(rni(div_fast(vb.y, bq.div)), qr.lo, qr.hi);
-        qb[2] = clampi(rni(div_fast(vb.z, bq.div)), qr.lo, qr.hi);
-        qb[3] = clampi(rni(div_fast(vb.w, bq.div)), qr.lo, qr.hi);
+      // ---- scale (fast: bound/qmax through the hoisted divide, fp16-normal result)
+      const float bound = max_nan(amax, 1e-9f);
+      uint16_t h16;
+      float scale = round_scale_bf16_f16(div_fast(bound, dq), &h16);
+      const bool fast = (clip == nullptr) && (bound <= 1.0e30f) && (scale >= 6.103515625e-05f) &&
+                        (scale <= 65504.0f);
+      uint32_t word_q0 = 0, word_q1 = 0, word_p = 0;
+      if (fast) {
+        const DivBy d = make_recip(scale);
+        const float t0 = div_fast(va.x, d), t1 = div_fast(va.y, d), t2 = div_fast(va.z, d),
+                    t3 = div_fast(va.w, d), t4_ = div_fast(vb.x, d), t5 = div_fast(vb.y, d),
+                    t6 = div_fast(vb.z, d), t7 = div_fast(vb.w, d);
+        if (OUT_P) {
+          const uint32_t ha = nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3));
+          const uint32_t hb = nibbles4_biased(rmagic8(t4_), rmagic8(t5), rmagic8(t6), rmagic8(t7));
+          word_p = __byte_perm(ha, hb, sel) ^ 0x88888888u;
+        }
+        if (OUT_Q) {
+          word_q0 = bytes4(rmagic(t0), rmagic(t1), rmagic(t2), rmagic(t3));
+          word_q1 = bytes4(rmagic(t4_), rmagic(t5), rmagic(t6), rmagic(t7));
+        }
       } else {
-        qa[0] = clampi(rni(__fdiv_rn(va.x, bq.scale)), qr.lo, qr.hi);
-        qa[1] = clampi(rni(__fdiv_rn(va.y, bq.scale)), qr.lo, qr.hi);
-        qa[2] = clampi(rni(__fdiv_rn(va.z, bq.scale)), qr.lo, qr.hi);
-        qa[3] = clampi(rni(__fdiv_rn(va.w, bq.scale)), qr.lo, qr.hi);
-        qb[0] = clampi(rni(__fdiv_rn(vb.x, bq.scale)), qr.lo, qr.hi);
-        qb[1] = clampi(rni(__fdiv_rn(vb.y, bq.scale)), qr.lo, qr.hi);
-        qb[2] = clampi(rni(__fdiv_rn(vb.z, bq.scale)), qr.lo, qr.hi);
-        qb[3] = clampi(rni(__fdiv_rn(vb.w, bq.scale)), qr.lo, qr.hi);
+        scale = block_scale_slow(amax, clip, blk0 + blk, b.bits, qr.qmax, &h16);
+        int qa[4], qb[4];
+        qa[0] = clampi(rni(__fdiv_rn(va.x, scale)), qr.lo, qr.hi);
+        qa[1] = clampi(rni(__fdiv_rn(va.y, scale)), qr.lo, qr.hi);
+        qa[2] = clampi(rni(__fdiv_rn(va.z, scale)), qr.lo, qr.hi);
+        qa[3] = clampi(rni(__fdiv_rn(va.w, scale)), qr.lo, qr.hi);
+        qb[0] = clampi(rni(__fdiv_rn(vb.x, scale)), qr.lo, qr.hi);
+        qb[1] = clampi(rni(__fdiv_rn(vb.y, scale)), qr.lo, qr.hi);
+        qb[2] = clampi(rni(__fdiv_rn(vb.z, scale)), qr.lo, qr.hi);
+        qb[3] = clampi(rni(__fdiv_rn(vb.w, scale)), qr.lo, qr.hi);
+        if (OUT_Q) {
+          word_q0 = pack_i8x4(qa[0], qa[1], qa[2], qa[3]);
+          word_q1 = pack_i8x4(qb[0], qb[1], qb[2], qb[3]);
+        }
+        if (OUT_P) {
+          const uint32_t ha = (qa[0] & 0xF) | ((qa[1] & 0xF) << 4) | ((qa[2] & 0xF) << 8) | ((qa[3] & 0xF) << 12);
+          const uint32_t hb = (qb[0] & 0xF) | ((qb[1] & 0xF) << 4) | ((qb[2] & 0xF) << 8) | ((qb[3] & 0xF) << 12);
+          word_p = __byte_perm(ha, hb, sel);
+        }
       }
-      const long long e = e0 + f0;
-      if (a.q) {
-        const uint32_t wa = pack_i8x4(qa[0], qa[1], qa[2], qa[3]);
-        const uint32_t wb = pack_i8x4(qb[0], qb[1], qb[2], qb[3]);
-        *reinterpret_cast<uint2*>(a.q + e) = sw ? make_uint2(wb, wa) : make_uint2(wa, wb);
-      }
-      if (a.packed) {  // bits == 4
-        const uint32_t ha = (qa[0] & 0xF) | ((qa[1] & 0xF) << 4) | ((qa[2] & 0xF) << 8) | ((qa[3] & 0xF) << 12);
-        const uint32_t hb = (qb[0] & 0xF) | ((qb[1] & 0xF) << 4) | ((qb[2] & 0xF) << 8) | ((qb[3] & 0xF) << 12);
-        *reinterpret_cast<uint32_t*>(a.packed + (e >> 1)) = sw ? (hb | (ha << 16)) : (ha | (hb << 16));
-      }
-      if ((lane & (LPB - 1)) == 0) {
-        if (a.scale) a.scale[blk] = bq.scale;
-        if (a.scale_f16) a.scale_f16[blk] = bq.f16;
-      }
+      if (OUT_Q)
+        *reinterpret_cast<uint2*>(qp + f0) = sw ? make_uint2(word_q1, word_q0) : make_uint2(word_q0, word_q1);
+      if (OUT_P) *reinterpret_cast<uint32_t*>(pp + (f0 >> 1)) = word_p;
+      if (w_scale) sp[blk0 + blk] = scale;
+      if (w_f16) hp[blk0 + blk] = h16;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -173,25 +204,27 @@ __global__ void __launch_bounds__((kNW + 1) * 32)
 }
 
 // Generic fallback: one warp per block, scalar global loads, any alignment.
-__global__ void __launch_bounds__(256) requant_blocks_generic(const __grid_constant__ BlocksArgs a) {
+__global__ void __launch_bounds__(256)
+    requant_blocks_generic(const BlocksJob a, int block, int bits) {
   const int lane = threadIdx.x & 31;
   const long long blk = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long n_blocks = a.n / a.block;
+  const long long n_blocks = a.n / block;
   if (blk >= n_blocks) return;
-  const QRange qr = qrange(a.bits, true);
-  const float* x = a.x + blk * a.block;
+  const QRange qr = qrange(bits, true);
+  const float* x = a.x + blk * block;
   float amax = 0.0f;
-  for (int i = lane; i < a.block; i += 32) amax = max_nan(amax, fabsf(x[i]));
+  for (int i = lane; i < block; i += 32) amax = max_nan(amax, fabsf(x[i]));
   amax = warp_max_nan(amax);
-  const BlockQ bq = finalize_block(a, blk, amax);
+  uint16_t h16;
+  const float scale = block_scale_slow(amax, a.clip, blk, bits, qr.qmax, &h16);
   if (lane == 0) {
-    if (a.scale) a.scale[blk] = bq.scale;
-    if (a.scale_f16) a.scale_f16[blk] = bq.f16;
+    if (a.scale) a.scale[blk] = scale;
+    if (a.scale_f16) a.scale_f16[blk] = h16;
   }
-  for (int i = lane * 2; i < a.block; i += 64) {
-    const int q0 = clampi(rni(div_any(x[i], bq.div)), qr.lo, qr.hi);
-    const int q1 = clampi(rni(div_any(x[i + 1], bq.div)), qr.lo, qr.hi);
-    const long long e = blk * a.block + i;
+  for (int i = lane * 2; i < block; i += 64) {
+    const int q0 = clampi(rni(__fdiv_rn(x[i], scale)), qr.lo, qr.hi);
+    const int q1 = clampi(rni(__fdiv_rn(x[i + 1], scale)), qr.lo, qr.hi);
+    const long long e = blk * block + i;
     if (a.q) {
       a.q[e] = static_cast<int8_t>(q0);
       a.q[e + 1] = static_cast<int8_t>(q1);
@@ -200,9 +233,9 @@ __global__ void __launch_bounds__(256) requant_blocks_generic(const __grid_const
   }
 }
 
-template <int BLOCK>
-cudaError_t launch_stream(BlocksArgs a, int sm_count, cudaStream_t st) {
-  auto kern = requant_blocks_stream<BLOCK>;
+template <int BLOCK, bool OUT_Q, bool OUT_P>
+cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
+  auto kern = requant_blocks_stream<BLOCK, OUT_Q, OUT_P>;
   const int smem = kStages * kStageBytes;
   static bool configured = false;
   if (!configured) {
@@ -210,33 +243,50 @@ cudaError_t launch_stream(BlocksArgs a, int sm_count, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  a.n_tiles = (a.n + kStageFloats - 1) / kStageFloats;
   long long grid = static_cast<long long>(sm_count) * 2;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  kern<<<static_cast<unsigned>(grid), (kNW + 1) * 32, smem, st>>>(a);
+  if (grid > b.n_tiles) grid = b.n_tiles;
+  kern<<<static_cast<unsigned>(grid), (kNW + 1) * 32, smem, st>>>(b);
   return cudaGetLastError();
+}
+
+template <int BLOCK>
+cudaError_t launch_stream_out(const BlocksBatch& b, bool out_q, bool out_p, int sm_count,
+                              cudaStream_t st) {
+  if (out_q && out_p) return launch_stream<BLOCK, true, true>(b, sm_count, st);
+  if (out_p) return launch_stream<BLOCK, false, true>(b, sm_count, st);
+  if (out_q) return launch_stream<BLOCK, true, false>(b, sm_count, st);
+  return launch_stream<BLOCK, false, false>(b, sm_count, st);  // scales only
 }
 
 }  // namespace
 
-cudaError_t launch_requant_blocks(BlocksArgs a, int sm_count, cudaStream_t st) {
-  if (a.n <= 0) return cudaSuccess;
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.x) % 16 == 0) &&
-                       (!a.q || reinterpret_cast<uintptr_t>(a.q) % 8 == 0) &&
-                       (!a.packed || reinterpret_cast<uintptr_t>(a.packed) % 4 == 0);
-  if (aligned) {
-    switch (a.block) {
-      case 32: return launch_stream<32>(a, sm_count, st);
-      case 64: return launch_stream<64>(a, sm_count, st);
-      case 128: return launch_stream<128>(a, sm_count, st);
-      case 256: return launch_stream<256>(a, sm_count, st);
-      default: break;
-    }
+long long blocks_job_tiles(long long n) { return (n + kStageFloats - 1) / kStageFloats; }
+
+bool blocks_job_streamable(const BlocksJob& j) {
+  return (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
+         (!j.q || reinterpret_cast<uintptr_t>(j.q) % 8 == 0) &&
+         (!j.packed || reinterpret_cast<uintptr_t>(j.packed) % 4 == 0);
+}
+
+cudaError_t launch_requant_blocks_stream(const BlocksBatch& b, bool out_q, bool out_p,
+                                         int sm_count, cudaStream_t st) {
+  if (b.n_tiles <= 0) return cudaSuccess;
+  switch (b.block) {
+    case 32: return launch_stream_out<32>(b, out_q, out_p, sm_count, st);
+    case 64: return launch_stream_out<64>(b, out_q, out_p, sm_count, st);
+    case 128: return launch_stream_out<128>(b, out_q, out_p, sm_count, st);
+    case 256: return launch_stream_out<256>(b, out_q, out_p, sm_count, st);
+    default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_requant_blocks_generic(const BlocksJob& j, int block, int bits,
+                                          cudaStream_t st) {
+  if (j.n <= 0) return cudaSuccess;
   const int warps = 8;
-  const long long n_blocks = a.n / a.block;
+  const long long n_blocks = j.n / block;
   const long long grid = (n_blocks + warps - 1) / warps;
-  requant_blocks_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(a);
+  requant_blocks_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(j, block, bits);
   return cudaGetLastError();
 }
 

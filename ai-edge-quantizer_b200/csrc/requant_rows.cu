@@ -11,12 +11,15 @@
 // over HBM: 4 B read + 1 B (or 0.5 B) written per weight.
 //
 // Tile-stream design (sm_100a): a persistent CTA owns every gridDim-th tile of
-// whole rows.  One producer lane keeps a 3-stage shared-memory ring full with
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); consumer warps
-// read the tile twice from shared memory (pass 1: NaN-propagating |x| max or
-// min&max per row; pass 2: exact divide, rint, clip, pack) so HBM is touched
-// once.  Rows are cut into 128-float warp chunks: a warp instruction reads 512
-// contiguous bytes (conflict-free LDS.128) and writes 128 contiguous bytes.
+// whole rows of a batch of tensors (job table passed by value in the kernel
+// parameters).  One producer lane keeps a 3-stage shared-memory ring full with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Rows are cut into
+// 128-float warp chunks; each consumer warp pulls its <= 8 chunks of the tile
+// into registers once (conflict-free LDS.128), reduces |x| max (or min & max)
+// per row with NaN propagation, merges across warps with shared-memory atomics,
+// and after one named barrier quantises from registers: hoisted exact divide
+// (3 FFMA), magic-number FADD for rint, PRMT byte packing, 128 contiguous bytes
+// written per warp instruction.  HBM is touched once, shared memory once.
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
@@ -26,7 +29,8 @@ namespace {
 
 constexpr int kStages = 3;
 constexpr int kMaxRowsPerTile = 64;
-constexpr int kChunk = 128;  // floats per warp chunk
+constexpr int kChunk = 128;   // floats per warp chunk
+constexpr int kMaxChunksPerWarp = 8;
 
 struct RowAcc {  // merged across warps with shared-memory atomics
   unsigned amax_bits;
@@ -34,25 +38,37 @@ struct RowAcc {  // merged across warps with shared-memory atomics
   int nan;
 };
 
-struct RowQ {  // per-row quantisation constants for pass 2
-  DivBy div;
-  float zp;
+enum RowMode : int {
+  kSlow = 0,       // IEEE divide, integer clamp (degenerate scales, unknown range)
+  kFastClamp = 1,  // hoisted divide + zero point + integer clamp
+  kFastSym = 2,    // hoisted divide + magic rounding, clamp provably idle
+};
+
+struct RowQ {  // per-row quantisation constants for pass 2 (16 bytes: one LDS.128)
+  float b, y, zp;
+  int mode;
+};
+
+struct StageDesc {
+  RowsJob job;
+  long long row0;
+  int nrows;
 };
 
 __device__ __forceinline__ void acc_reset(RowAcc& a) {
   a.amax_bits = 0u;
-  a.mn_ord = 0x7f800000;             // f2ord(+inf)
-  a.mx_ord = (int)0x807fffff;        // f2ord(-inf)
+  a.mn_ord = 0x7f800000;       // f2ord(+inf)
+  a.mx_ord = (int)0x807fffff;  // f2ord(-inf)
   a.nan = 0;
 }
 
 // uqt:492-586 for one row.  `xmax` bounds |x| over the row (for the divide
-// window); pass +inf when unknown.
-__device__ __forceinline__ RowQ finalize_row(const RowsArgs& a, long long row, float mn, float mx,
-                                            float xmax) {
-  const QRange qr = qrange(a.bits, a.symmetric != 0);
+// window); pass +inf when the row was not scanned.
+__device__ __forceinline__ RowQ finalize_row(const RowsJob& a, int bits, bool sym, long long row,
+                                            float mn, float mx, float xmax, bool publish) {
+  const QRange qr = qrange(bits, sym);
   float scale, zpf = 0.0f;
-  if (a.symmetric) {
+  if (sym) {
     float bound = max_nan(max_nan(fabsf(mn), fabsf(mx)), 1e-9f);
     if (a.clip) {
       const float c = a.clip[row * a.clip_stride];
@@ -70,38 +86,49 @@ __device__ __forceinline__ RowQ finalize_row(const RowsArgs& a, long long row, f
     scale = __fdiv_rn(bound, __fsub_rn(qr.qmax, qr.qmin));
     zpf = rintf(__fsub_rn(qr.qmin, __fdiv_rn(bmin, scale)));
   }
-  if (a.scale) a.scale[row * a.out_stride] = scale;
-  if (a.zp) a.zp[row * a.out_stride] = rni(zpf);
+  // uqt:585: the zero point is cast to the quantised dtype (int8 for <= 8 bits)
+  // without clipping, i.e. it wraps; identity unless a clip shrank the range.
+  const int zpi = static_cast<int>(static_cast<int8_t>(rni(zpf)));
+  if (publish) {
+    if (a.scale) a.scale[row * a.out_stride] = scale;
+    if (a.zp) a.zp[row * a.out_stride] = zpi;
+  }
   RowQ r;
-  r.div = make_div(scale, xmax);
-  // int8 cast of the zero point (uqt:585) is the identity for finite inputs.
-  r.zp = static_cast<float>(rni(zpf));
+  const DivBy d = make_div(scale, xmax);
+  r.b = scale;
+  r.y = d.y;
+  r.zp = static_cast<float>(zpi);
+  const bool clamp_idle = sym && a.clip == nullptr && a.given_min == nullptr;
+  r.mode = !d.fast ? kSlow : (clamp_idle ? kFastSym : kFastClamp);
   return r;
 }
 
-__device__ __forceinline__ int quant1(float x, const RowQ& rq, bool sym, int lo, int hi) {
-  float t = div_any(x, rq.div);
+__device__ __forceinline__ int quant_slow(float x, const RowQ& rq, bool sym, int lo, int hi) {
+  float t = __fdiv_rn(x, rq.b);
   if (!sym) t = __fadd_rn(t, rq.zp);
   return clampi(rni(t), lo, hi);
 }
 
+__device__ __forceinline__ float div_row(float x, const RowQ& rq) {
+  const float q0 = x * rq.y;
+  return fmaf(rq.y, fmaf(-rq.b, q0, x), q0);
+}
+
 // ------------------------------------------------------------------ TMA tile stream
 template <int STAGE_BYTES, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32)
-    requant_rows_stream(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
+    requant_rows_stream(const __grid_constant__ RowsBatch b) {
+  static_assert(STAGE_BYTES / (kChunk * 4) == NW * kMaxChunksPerWarp, "chunks per warp");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ RowAcc s_acc[2][kMaxRowsPerTile];
-  __shared__ RowQ s_rq[kMaxRowsPerTile];
+  __shared__ StageDesc desc[kStages];
+  __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int cols = a.cols;
-  const int cpr = cols / kChunk;
-  const int rpt = a.rows_per_tile;
-  const long long n_tiles = a.n_tiles;
+  const long long n_tiles = b.n_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -110,21 +137,27 @@ __global__ void __launch_bounds__((NW + 1) * 32)
     }
     mbar_fence_init();
   }
-  if (tid < 2 * kMaxRowsPerTile) acc_reset(s_acc[tid / kMaxRowsPerTile][tid % kMaxRowsPerTile]);
+  if (tid < 3 * kMaxRowsPerTile) acc_reset(s_acc[tid / kMaxRowsPerTile][tid % kMaxRowsPerTile]);
   __syncthreads();
 
   if (warp == NW) {  // ---------------- producer
     if (lane == 0) {
+      int j = 0;
+      RowsJob job = b.jobs[0];
       long long it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = static_cast<int>(it % kStages);
         const long long round = it / kStages;
         if (round > 0) mbar_wait(&empty_bar[s], static_cast<uint32_t>((round - 1) & 1));
-        const long long row0 = tile * rpt;
-        const long long nrows = min(static_cast<long long>(rpt), a.rows - row0);
-        const uint32_t bytes = static_cast<uint32_t>(nrows * cols * 4);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(smem_raw + static_cast<size_t>(s) * STAGE_BYTES, a.x + row0 * cols, bytes,
+        while (tile >= job.tile_end) job = b.jobs[++j];
+        const long long row0 = (tile - job.tile0) * job.rows_per_tile;
+        const long long nrows = min(static_cast<long long>(job.rows_per_tile), job.rows - row0);
+        desc[s].job = job;
+        desc[s].row0 = row0;
+        desc[s].nrows = static_cast<int>(nrows);
+        const uint32_t bytes = static_cast<uint32_t>(nrows * job.cols * 4);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);  // release: desc visible to waiters
+        bulk_g2s(smem_raw + static_cast<size_t>(s) * STAGE_BYTES, job.x + row0 * job.cols, bytes,
                  &full_bar[s]);
       }
     }
@@ -132,26 +165,32 @@ __global__ void __launch_bounds__((NW + 1) * 32)
   }
 
   // ---------------- consumers
-  const bool sym = a.symmetric != 0;
-  const bool given = a.given_min != nullptr;
-  const QRange qr = qrange(a.bits, sym);
+  const bool sym = b.symmetric != 0;
+  const int bits = b.bits;
+  const QRange qr = qrange(bits, sym);
   long long it = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int s = static_cast<int>(it % kStages);
     const uint32_t ph = static_cast<uint32_t>((it / kStages) & 1);
-    const int buf = static_cast<int>(it & 1);
-    const long long row0 = tile * rpt;
-    const int nrows = static_cast<int>(min(static_cast<long long>(rpt), a.rows - row0));
-    const int nchunks = nrows * cpr;
+    const int buf = static_cast<int>(it % 3);
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * STAGE_BYTES);
 
     mbar_wait(&full_bar[s], ph);
 
-    // ---- pass 1: per-row statistics
-    if (!given) {
-      int row = 0, rem = warp;
-      while (rem >= cpr) { rem -= cpr; ++row; }
-      int cur = row;
+    const RowsJob& job = desc[s].job;
+    const long long row0 = desc[s].row0;
+    const int nrows = desc[s].nrows;
+    const int cols = job.cols;
+    const int cpr = cols / kChunk;
+    const int nchunks = nrows * cpr;
+    const bool given = job.given_min != nullptr;
+
+    // ---- pass 1: pull this warp's chunks into registers, per-row statistics
+    float4 v[kMaxChunksPerWarp];
+    int row_start = 0, rem_start = warp;
+    while (rem_start >= cpr) { rem_start -= cpr; ++row_start; }
+    {
+      int row = row_start, rem = rem_start, cur = row_start;
       bool any = false;
       float amax = 0.0f, mn = INFINITY, mx = -INFINITY;
       auto flush = [&](int r) {
@@ -170,108 +209,145 @@ __global__ void __launch_bounds__((NW + 1) * 32)
           }
         }
       };
-      for (int c = warp; c < nchunks; c += NW) {
-        if (row != cur) {
-          flush(cur);
-          cur = row;
-          amax = 0.0f; mn = INFINITY; mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+        const int c = warp + j * NW;
+        if (c < nchunks) {
+          v[j] = t4[c * 32 + lane];
+          if (!given) {
+            if (row != cur) {
+              flush(cur);
+              cur = row;
+              amax = 0.0f; mn = INFINITY; mx = -INFINITY;
+            }
+            if (sym) {
+              amax = absmax4(amax, v[j]);
+            } else {
+              mn = min_nan(min_nan(mn, v[j].x), min_nan(v[j].y, min_nan(v[j].z, v[j].w)));
+              mx = max_nan(max_nan(mx, v[j].x), max_nan(v[j].y, max_nan(v[j].z, v[j].w)));
+            }
+            any = true;
+            rem += NW;
+            while (rem >= cpr) { rem -= cpr; ++row; }
+          }
         }
-        const float4 v = t4[c * 32 + lane];
-        if (sym) {
-          amax = absmax4(amax, v);
-        } else {
-          mn = min_nan(min_nan(mn, v.x), min_nan(v.y, min_nan(v.z, v.w)));
-          mx = max_nan(max_nan(mx, v.x), max_nan(v.y, max_nan(v.z, v.w)));
-        }
-        any = true;
-        rem += NW;
-        while (rem >= cpr) { rem -= cpr; ++row; }
       }
       if (any) flush(cur);
     }
-    named_bar_sync(1, NW * 32);
+    // Everything pass 2 needs from the stage descriptor is copied to registers,
+    // then the stage goes back to the producer early: the tile lives in registers.
+    int8_t* const qp = job.q ? job.q + row0 * cols : nullptr;
+    uint8_t* const pp = job.packed ? job.packed + ((row0 * cols * bits) >> 3) : nullptr;
+    // Lane l < 8 will finalise the row of this warp's l-th chunk: it needs the job.
+    const int my_c = warp + (lane & 7) * NW;
+    const bool my_valid = lane < kMaxChunksPerWarp && my_c < nchunks;
+    RowsJob jcopy;
+    if (my_valid) jcopy = job;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // asm volatile + memory clobber: no smem read sinks below
+    named_bar_sync(1, NW * 32);  // every warp's partials are merged in s_acc[buf]
 
-    // ---- per-row scale / zero point
-    if (tid < nrows) {
-      const long long grow = row0 + tid;
+    // ---- per-row scale / zero point, one lane per chunk slot (no second barrier):
+    // the row's first chunk owner publishes scale / zp to global memory.
+    RowQ mine;
+    mine.b = 1.0f; mine.y = 1.0f; mine.zp = 0.0f; mine.mode = kSlow;
+    if (my_valid) {
+      const int r = my_c / cpr;
+      const long long grow = row0 + r;
       float mn, mx, xmax;
       if (given) {
-        mn = a.given_min[grow * a.mm_stride];
-        mx = a.given_max[grow * a.mm_stride];
+        mn = jcopy.given_min[grow * jcopy.mm_stride];
+        mx = jcopy.given_max[grow * jcopy.mm_stride];
         xmax = INFINITY;  // row not scanned: always take the IEEE divide
       } else if (sym) {
-        mx = __uint_as_float(s_acc[buf][tid].amax_bits);
+        mx = __uint_as_float(s_acc[buf][r].amax_bits);
         mn = -mx;
         xmax = mx;
       } else {
-        const RowAcc acc = s_acc[buf][tid];
+        const RowAcc acc = s_acc[buf][r];
         mn = acc.nan ? NAN : ord2f(acc.mn_ord);
         mx = acc.nan ? NAN : ord2f(acc.mx_ord);
         xmax = max_nan(fabsf(mn), fabsf(mx));
       }
-      s_rq[tid] = finalize_row(a, grow, mn, mx, xmax);
+      mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c % cpr == 0);
     }
-    if (tid < kMaxRowsPerTile) acc_reset(s_acc[buf ^ 1][tid]);
-    named_bar_sync(1, NW * 32);
+    // Buffer (it+2)%3 was last read during the previous tile, which every warp has
+    // left (they all passed the barrier above); it is next written two tiles from now.
+    if (tid < kMaxRowsPerTile) acc_reset(s_acc[(buf + 2) % 3][tid]);
 
-    // ---- pass 2: quantise + store
+    // ---- pass 2: quantise from registers + store
     {
-      int row = 0, rem = warp;
-      while (rem >= cpr) { rem -= cpr; ++row; }
-      const long long tile_elem0 = row0 * cols;
-      for (int c = warp; c < nchunks; c += NW) {
-        const RowQ rq = s_rq[row];
-        const float4 v = t4[c * 32 + lane];
-        int q0, q1, q2, q3;
-        if (rq.div.fast && sym) {
-          q0 = clampi(rni(div_fast(v.x, rq.div)), qr.lo, qr.hi);
-          q1 = clampi(rni(div_fast(v.y, rq.div)), qr.lo, qr.hi);
-          q2 = clampi(rni(div_fast(v.z, rq.div)), qr.lo, qr.hi);
-          q3 = clampi(rni(div_fast(v.w, rq.div)), qr.lo, qr.hi);
-        } else {
-          q0 = quant1(v.x, rq, sym, qr.lo, qr.hi);
-          q1 = quant1(v.y, rq, sym, qr.lo, qr.hi);
-          q2 = quant1(v.z, rq, sym, qr.lo, qr.hi);
-          q3 = quant1(v.w, rq, sym, qr.lo, qr.hi);
-        }
-        const long long e = tile_elem0 + static_cast<long long>(c) * kChunk + lane * 4;
-        if (a.q) *reinterpret_cast<uint32_t*>(a.q + e) = pack_i8x4(q0, q1, q2, q3);
-        if (a.packed) {
-          if (a.bits == 4) {
-            uint32_t h = (q0 & 0xF) | ((q1 & 0xF) << 4) | ((q2 & 0xF) << 8) | ((q3 & 0xF) << 12);
-            const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
-            if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(a.packed + e / 2) = h | (o << 16);
-          } else {  // bits == 2
-            uint32_t b = (q0 & 3) | ((q1 & 3) << 2) | ((q2 & 3) << 4) | ((q3 & 3) << 6);
-            const uint32_t o1 = __shfl_down_sync(0xffffffffu, b, 1);
-            const uint32_t o2 = __shfl_down_sync(0xffffffffu, b, 2);
-            const uint32_t o3 = __shfl_down_sync(0xffffffffu, b, 3);
-            if ((lane & 3) == 0)
-              *reinterpret_cast<uint32_t*>(a.packed + e / 4) = b | (o1 << 8) | (o2 << 16) | (o3 << 24);
+#pragma unroll
+      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+        const int c = warp + j * NW;
+        RowQ rq;
+        rq.b = __shfl_sync(0xffffffffu, mine.b, j);
+        rq.y = __shfl_sync(0xffffffffu, mine.y, j);
+        rq.zp = __shfl_sync(0xffffffffu, mine.zp, j);
+        rq.mode = __shfl_sync(0xffffffffu, mine.mode, j);
+        if (c < nchunks) {
+          const long long e = static_cast<long long>(c) * kChunk + lane * 4;  // inside the tile
+          if (rq.mode == kFastSym && !(pp && bits == 2)) {
+            const float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq),
+                        t2 = div_row(v[j].z, rq), t3 = div_row(v[j].w, rq);
+            if (qp) *reinterpret_cast<uint32_t*>(qp + e) = bytes4(rmagic(t0), rmagic(t1), rmagic(t2), rmagic(t3));
+            if (pp) {  // bits == 4
+              const uint32_t h =
+                  (nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3)) ^ 0x8888u) & 0xFFFFu;
+              const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
+              if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(pp + (e >> 1)) = h | (o << 16);
+            }
+          } else {
+            int q0, q1, q2, q3;
+            if (rq.mode != kSlow) {
+              float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq), t2 = div_row(v[j].z, rq),
+                    t3 = div_row(v[j].w, rq);
+              if (!sym) {
+                t0 = __fadd_rn(t0, rq.zp); t1 = __fadd_rn(t1, rq.zp);
+                t2 = __fadd_rn(t2, rq.zp); t3 = __fadd_rn(t3, rq.zp);
+              }
+              q0 = clampi(rni(t0), qr.lo, qr.hi); q1 = clampi(rni(t1), qr.lo, qr.hi);
+              q2 = clampi(rni(t2), qr.lo, qr.hi); q3 = clampi(rni(t3), qr.lo, qr.hi);
+            } else {
+              q0 = quant_slow(v[j].x, rq, sym, qr.lo, qr.hi);
+              q1 = quant_slow(v[j].y, rq, sym, qr.lo, qr.hi);
+              q2 = quant_slow(v[j].z, rq, sym, qr.lo, qr.hi);
+              q3 = quant_slow(v[j].w, rq, sym, qr.lo, qr.hi);
+            }
+            if (qp) *reinterpret_cast<uint32_t*>(qp + e) = pack_i8x4(q0, q1, q2, q3);
+            if (pp) {
+              if (bits == 4) {
+                const uint32_t h = (q0 & 0xF) | ((q1 & 0xF) << 4) | ((q2 & 0xF) << 8) | ((q3 & 0xF) << 12);
+                const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
+                if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(pp + (e >> 1)) = h | (o << 16);
+              } else {  // bits == 2
+                const uint32_t by = (q0 & 3) | ((q1 & 3) << 2) | ((q2 & 3) << 4) | ((q3 & 3) << 6);
+                const uint32_t o1 = __shfl_down_sync(0xffffffffu, by, 1);
+                const uint32_t o2 = __shfl_down_sync(0xffffffffu, by, 2);
+                const uint32_t o3 = __shfl_down_sync(0xffffffffu, by, 3);
+                if ((lane & 3) == 0)
+                  *reinterpret_cast<uint32_t*>(pp + (e >> 2)) = by | (o1 << 8) | (o2 << 16) | (o3 << 24);
+              }
+            }
           }
         }
-        rem += NW;
-        while (rem >= cpr) { rem -= cpr; ++row; }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
 }
 
 // ------------------------------------------------------------------ generic fallback
 // One warp per row, scalar loads straight from global, two passes (the second
 // one normally hits L2).  Any cols, any alignment.  Packed output is written
-// bytewise: a byte never straddles two lanes because each lane owns aligned
-// groups of 8/bits consecutive elements; packing is over the FLAT tensor
-// (pack_data ravel()s first), so a byte may straddle two rows when cols is
-// odd — those tensors go through aeqb_pack_bits instead (host side decides).
-__global__ void __launch_bounds__(256) requant_rows_generic(const __grid_constant__ RowsArgs a) {
+// bytewise; packing is over the FLAT tensor (pack_data ravel()s first), so the
+// launcher only allows it when a byte cannot straddle two rows.
+__global__ void __launch_bounds__(256)
+    requant_rows_generic(const RowsJob a, int bits, int symmetric) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= a.rows) return;
-  const bool sym = a.symmetric != 0;
-  const QRange qr = qrange(a.bits, sym);
+  const bool sym = symmetric != 0;
+  const QRange qr = qrange(bits, sym);
   const float* x = a.x + row * a.cols;
   float mn, mx, xmax;
   if (a.given_min) {
@@ -290,23 +366,22 @@ __global__ void __launch_bounds__(256) requant_rows_generic(const __grid_constan
     mx = warp_max_nan(mx);
     xmax = max_nan(fabsf(mn), fabsf(mx));
   }
-  RowsArgs b = a;  // only lane 0 publishes scale / zp
-  if (lane != 0) { b.scale = nullptr; b.zp = nullptr; }
-  const RowQ rq = finalize_row(b, row, mn, mx, xmax);
-  const int per = a.packed ? 8 / a.bits : 1;  // elements per packed byte
+  RowQ rq = finalize_row(a, bits, sym, row, mn, mx, xmax, lane == 0);
+  rq.mode = kSlow;
+  const int per = a.packed ? 8 / bits : 1;  // elements per packed byte
   for (int c0 = lane * per; c0 < a.cols; c0 += 32 * per) {
     unsigned byte = 0;
     for (int j = 0; j < per && c0 + j < a.cols; ++j) {
-      const int q = quant1(x[c0 + j], rq, sym, qr.lo, qr.hi);
+      const int q = quant_slow(x[c0 + j], rq, sym, qr.lo, qr.hi);
       if (a.q) a.q[row * a.cols + c0 + j] = static_cast<int8_t>(q);
-      byte |= (static_cast<unsigned>(q) & ((1u << a.bits) - 1u)) << (a.bits * j);
+      byte |= (static_cast<unsigned>(q) & ((1u << bits) - 1u)) << (bits * j);
     }
     if (a.packed) a.packed[(row * a.cols + c0) / per] = static_cast<uint8_t>(byte);
   }
 }
 
 template <int STAGE_BYTES, int NW>
-cudaError_t launch_stream(RowsArgs a, int sm_count, int ctas_per_sm, cudaStream_t st) {
+cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
   auto kern = requant_rows_stream<STAGE_BYTES, NW>;
   const int smem = kStages * STAGE_BYTES;
   static bool configured = false;
@@ -315,34 +390,46 @@ cudaError_t launch_stream(RowsArgs a, int sm_count, int ctas_per_sm, cudaStream_
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const long long row_bytes = static_cast<long long>(a.cols) * 4;
-  int rpt = static_cast<int>(STAGE_BYTES / row_bytes);
-  if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
-  a.rows_per_tile = rpt;
-  a.n_tiles = (a.rows + rpt - 1) / rpt;
   long long grid = static_cast<long long>(sm_count) * ctas_per_sm;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(a);
+  if (grid > b.n_tiles) grid = b.n_tiles;
+  kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_requant_rows(RowsArgs a, int sm_count, cudaStream_t st) {
-  if (a.rows <= 0 || a.cols <= 0) return cudaSuccess;
-  const long long row_bytes = static_cast<long long>(a.cols) * 4;
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.x) % 16 == 0) &&
-                       (!a.q || reinterpret_cast<uintptr_t>(a.q) % 4 == 0) &&
-                       (!a.packed || reinterpret_cast<uintptr_t>(a.packed) % 4 == 0);
-  const bool packed_rows_ok = !a.packed || (a.cols % (8 / a.bits) == 0);
-  if (aligned && a.cols % kChunk == 0 && row_bytes <= 32768)
-    return launch_stream<32768, 8>(a, sm_count, 2, st);
-  if (aligned && a.cols % kChunk == 0 && row_bytes <= 65536)
-    return launch_stream<65536, 16>(a, sm_count, 1, st);
-  if (!packed_rows_ok) return cudaErrorInvalidValue;  // caller packs separately
+int rows_job_class(const RowsJob& j, int bits) {
+  const long long row_bytes = static_cast<long long>(j.cols) * 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
+                       (!j.q || reinterpret_cast<uintptr_t>(j.q) % 4 == 0) &&
+                       (!j.packed || reinterpret_cast<uintptr_t>(j.packed) % 4 == 0);
+  (void)bits;
+  if (aligned && j.cols % kChunk == 0 && row_bytes <= 32768) return 1;
+  if (aligned && j.cols % kChunk == 0 && row_bytes <= 65536) return 2;
+  return 0;
+}
+
+int rows_job_rows_per_tile(const RowsJob& j, int klass) {
+  const long long stage = klass == 1 ? 32768 : 65536;
+  long long rpt = stage / (static_cast<long long>(j.cols) * 4);
+  if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
+  return static_cast<int>(rpt);
+}
+
+cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count,
+                                       cudaStream_t st) {
+  if (b.n_tiles <= 0) return cudaSuccess;
+  if (klass == 1) return launch_stream<32768, 8>(b, sm_count, 2, st);
+  return launch_stream<65536, 16>(b, sm_count, 1, st);
+}
+
+cudaError_t launch_requant_rows_generic(const RowsJob& j, int bits, int symmetric,
+                                        cudaStream_t st) {
+  if (j.rows <= 0 || j.cols <= 0) return cudaSuccess;
+  if (j.packed && (j.cols % (8 / bits) != 0)) return cudaErrorInvalidValue;  // caller packs separately
   const int warps = 8;
-  const long long grid = (a.rows + warps - 1) / warps;
-  requant_rows_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(a);
+  const long long grid = (j.rows + warps - 1) / warps;
+  requant_rows_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(j, bits, symmetric);
   return cudaGetLastError();
 }
 

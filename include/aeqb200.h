@@ -78,6 +78,39 @@ AEQB_API int aeqb_requant_blocks_f32(const float* x, int64_t rows, int64_t cols,
                             const float* clip, int8_t* q, uint8_t* packed, float* scale,
                             uint16_t* scale_f16, void* stream);
 
+/* ---------------------------------------------------------------- weights, batched
+ * A whole model's weight buffers in one call: every tensor that qualifies for
+ * the tile-stream kernels is folded into persistent launches of up to 64 tensors
+ * (the job table travels in the kernel parameters: no workspace, no extra copy,
+ * no per-tensor launch ramp).  This is the device side of the batched driver
+ * that sits behind params_generator.generate_quantization_parameters
+ * (params_generator.py:69-185).  `jobs` is a HOST array; the pointers inside are
+ * device pointers with the meaning of the single-tensor entry points above. */
+typedef struct aeqb_rows_job {
+  const float* x;
+  int64_t rows, cols;
+  const float* clip; /* optional [rows] */
+  int8_t* q;         /* optional [rows*cols] */
+  uint8_t* packed;   /* optional [rows*cols*bits/8] */
+  float* scale;      /* optional [rows] */
+  int32_t* zp;       /* optional [rows] */
+} aeqb_rows_job;
+
+typedef struct aeqb_blocks_job {
+  const float* x;
+  int64_t rows, cols;
+  const float* clip;   /* optional [rows*cols/block] */
+  int8_t* q;           /* optional [rows*cols] */
+  uint8_t* packed;     /* optional [rows*cols/2], bits == 4 */
+  float* scale;        /* optional [rows*cols/block] */
+  uint16_t* scale_f16; /* optional [rows*cols/block] fp16 bits */
+} aeqb_blocks_job;
+
+AEQB_API int aeqb_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
+                                         int symmetric, void* stream);
+AEQB_API int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block,
+                                           int bits, void* stream);
+
 /* ---------------------------------------------------------------- statistics
  * Whole-tensor min/max with the open-interval validity filter and raw fallback:
  * out2[0] = min{x : x > lo} (raw NaN-propagating min when nothing passes or

@@ -60,13 +60,23 @@ def main():
       lib.aeqb_requant_blocks_f32(ws[i].data_ptr(), R, C, 32, 4, None, q[i].data_ptr(), None,
                                   bs[i].data_ptr(), None, st)
 
+  from aeq_b200 import device
+  state = {}
+
+  def rows8_batch():
+    state["r8"] = device.requant_rows_batch(ws, 8, True, outs=state.get("r8"))
+
+  def blk4p_batch():
+    state["b4"] = device.requant_blocks_batch(ws, 32, 4, outs=state.get("b4"))
+
   def copy():
     for i in range(T):
       q[i].view(torch.float32).copy_(ws[i].view(-1)[: R * C // 4].view(R, C // 4))
 
   n = R * C * T
   cases = [("rows_int8", rows8, 5.0), ("rows_int4_packed", rows4p, 4.5),
-           ("blocks32_int4_packed", blk4p, 4.5625), ("blocks32_int4_unpacked", blk4q, 5.125)]
+           ("blocks32_int4_packed", blk4p, 4.5625), ("blocks32_int4_unpacked", blk4q, 5.125),
+           ("rows_int8_batch", rows8_batch, 5.0), ("blocks32_int4_packed_batch", blk4p_batch, 4.5625)]
   for name, fn, bpw in cases:
     for _ in range(3):
       fn()
