@@ -69,6 +69,7 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
       aeqb::RowsJob j = jobs[i];
       if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != klass) continue;
       j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
+      j.cpr_magic = static_cast<unsigned>(((1u << 20) + (j.cols / 128) - 1) / (j.cols / 128));
       j.tile0 = b.n_tiles;
       j.tile_end = j.tile0 + (j.rows + j.rows_per_tile - 1) / j.rows_per_tile;
       b.n_tiles = j.tile_end;

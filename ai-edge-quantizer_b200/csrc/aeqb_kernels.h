@@ -23,6 +23,7 @@ struct RowsJob {
   long long rows;
   int cols;
   int rows_per_tile;            // launcher
+  unsigned cpr_magic;           // launcher: ceil(2^20 / (cols/128)), row = (chunk*magic)>>20
   int mm_stride, clip_stride;   // 0: one value for the whole tensor, 1: per row
   int out_stride;
   long long tile0, tile_end;    // this job's tile range inside the batch (launcher)

@@ -185,54 +185,37 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     const int nchunks = nrows * cpr;
     const bool given = job.given_min != nullptr;
 
-    // ---- pass 1: pull this warp's chunks into registers, per-row statistics
+    // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
+    // atomic per chunk merges the row statistics (no row-change bookkeeping).
+    const unsigned magic = job.cpr_magic;  // row of chunk c = (c * magic) >> 20
     float4 v[kMaxChunksPerWarp];
-    int row_start = 0, rem_start = warp;
-    while (rem_start >= cpr) { rem_start -= cpr; ++row_start; }
-    {
-      int row = row_start, rem = rem_start, cur = row_start;
-      bool any = false;
-      float amax = 0.0f, mn = INFINITY, mx = -INFINITY;
-      auto flush = [&](int r) {
-        if (sym) {
-          const float m = warp_max_nan(amax);
-          if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, __float_as_uint(m));
-        } else {
-          const float lo = warp_min_nan(mn), hi = warp_max_nan(mx);
-          if (lane == 0) {
-            if (lo != lo || hi != hi) {
-              atomicOr(&s_acc[buf][r].nan, 1);
-            } else {
-              atomicMin(&s_acc[buf][r].mn_ord, f2ord(lo));
-              atomicMax(&s_acc[buf][r].mx_ord, f2ord(hi));
-            }
-          }
-        }
-      };
 #pragma unroll
-      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
-        const int c = warp + j * NW;
-        if (c < nchunks) {
-          v[j] = t4[c * 32 + lane];
-          if (!given) {
-            if (row != cur) {
-              flush(cur);
-              cur = row;
-              amax = 0.0f; mn = INFINITY; mx = -INFINITY;
+    for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+      const int c = warp + j * NW;
+      if (c < nchunks) {
+        v[j] = t4[c * 32 + lane];
+        if (!given) {
+          const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
+          if (sym) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
+            if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
+          } else {
+            const float lo = min_nan(min_nan(v[j].x, v[j].y), min_nan(v[j].z, v[j].w));
+            const float hi = max_nan(max_nan(v[j].x, v[j].y), max_nan(v[j].z, v[j].w));
+            const bool bad = __any_sync(0xffffffffu, lo != lo);
+            const int mn = __reduce_min_sync(0xffffffffu, f2ord(lo));
+            const int mx = __reduce_max_sync(0xffffffffu, f2ord(hi));
+            if (lane == 0) {
+              if (bad) {
+                atomicOr(&s_acc[buf][r].nan, 1);
+              } else {
+                atomicMin(&s_acc[buf][r].mn_ord, mn);
+                atomicMax(&s_acc[buf][r].mx_ord, mx);
+              }
             }
-            if (sym) {
-              amax = absmax4(amax, v[j]);
-            } else {
-              mn = min_nan(min_nan(mn, v[j].x), min_nan(v[j].y, min_nan(v[j].z, v[j].w)));
-              mx = max_nan(max_nan(mx, v[j].x), max_nan(v[j].y, max_nan(v[j].z, v[j].w)));
-            }
-            any = true;
-            rem += NW;
-            while (rem >= cpr) { rem -= cpr; ++row; }
           }
         }
       }
-      if (any) flush(cur);
     }
     // Everything pass 2 needs from the stage descriptor is copied to registers,
     // then the stage goes back to the producer early: the tile lives in registers.
@@ -252,7 +235,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     RowQ mine;
     mine.b = 1.0f; mine.y = 1.0f; mine.zp = 0.0f; mine.mode = kSlow;
     if (my_valid) {
-      const int r = my_c / cpr;
+      const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
       float mn, mx, xmax;
       if (given) {
@@ -269,7 +252,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
         mx = acc.nan ? NAN : ord2f(acc.mx_ord);
         xmax = max_nan(fabsf(mn), fabsf(mx));
       }
-      mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c % cpr == 0);
+      mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c == r * cpr);
     }
     // Buffer (it+2)%3 was last read during the previous tile, which every warp has
     // left (they all passed the barrier above); it is next written two tiles from now.
@@ -286,7 +269,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
         rq.zp = __shfl_sync(0xffffffffu, mine.zp, j);
         rq.mode = __shfl_sync(0xffffffffu, mine.mode, j);
         if (c < nchunks) {
-          const long long e = static_cast<long long>(c) * kChunk + lane * 4;  // inside the tile
+          const int e = c * kChunk + lane * 4;  // inside the tile
           if (rq.mode == kFastSym && !(pp && bits == 2)) {
             const float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq),
                         t2 = div_row(v[j].z, rq), t3 = div_row(v[j].w, rq);

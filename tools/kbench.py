@@ -22,6 +22,7 @@ def main():
   ap.add_argument("--cols", type=int, default=4096)
   ap.add_argument("--tensors", type=int, default=64)
   ap.add_argument("--iters", type=int, default=20)
+  ap.add_argument("--only", default="")
   a = ap.parse_args()
   peak = 6558.1
   try:
@@ -78,6 +79,8 @@ def main():
            ("blocks32_int4_packed", blk4p, 4.5625), ("blocks32_int4_unpacked", blk4q, 5.125),
            ("rows_int8_batch", rows8_batch, 5.0), ("blocks32_int4_packed_batch", blk4p_batch, 4.5625)]
   for name, fn, bpw in cases:
+    if a.only and name not in a.only.split(","):
+      continue
     for _ in range(3):
       fn()
     torch.cuda.synchronize()
