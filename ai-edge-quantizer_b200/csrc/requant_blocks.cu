@@ -93,11 +93,10 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
     if (lane == 0) {
       int j = 0;
       BlocksJob job = b.jobs[0];
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = static_cast<int>(it % kStages);
-        const long long round = it / kStages;
-        if (round > 0) mbar_wait(&empty_bar[s], static_cast<uint32_t>((round - 1) & 1));
+      int s = 0;
+      uint32_t round = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
         while (tile >= job.tile_end) job = b.jobs[++j];
         const long long e0 = (tile - job.tile0) * kStageFloats;
         const long long ne = min(static_cast<long long>(kStageFloats), job.n - e0);
@@ -107,6 +106,7 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
         const uint32_t bytes = static_cast<uint32_t>(ne * 4);
         mbar_arrive_expect_tx(&full_bar[s], bytes);  // release: desc is visible to waiters
         bulk_g2s(smem_raw + static_cast<size_t>(s) * kStageBytes, job.x + e0, bytes, &full_bar[s]);
+        if (++s == kStages) { s = 0; ++round; }
       }
     }
     return;
@@ -118,10 +118,11 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
   const int sw = (lane >> 2) & 1;            // load-order swizzle
   const uint32_t sel = sw ? 0x1054u : 0x5410u;  // PRMT: which float4 holds the low elements
   const bool leader = (lane & (LPB - 1)) == 0;
-  long long it = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = static_cast<int>(it % kStages);
-    const uint32_t ph = static_cast<uint32_t>((it / kStages) & 1);
+  int s = -1;
+  uint32_t ph = 1;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (++s == kStages) s = 0;
+    if (s == 0) ph ^= 1;
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * kStageBytes);
 
     mbar_wait(&full_bar[s], ph);

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ StageDesc desc[kStages];
   __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
+  __shared__ float2 s_by[NW][kMaxChunksPerWarp];  // per-warp (scale, reciprocal) of each chunk slot
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -144,11 +145,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     if (lane == 0) {
       int j = 0;
       RowsJob job = b.jobs[0];
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = static_cast<int>(it % kStages);
-        const long long round = it / kStages;
-        if (round > 0) mbar_wait(&empty_bar[s], static_cast<uint32_t>((round - 1) & 1));
+      int s = 0;
+      uint32_t round = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
         while (tile >= job.tile_end) job = b.jobs[++j];
         const long long row0 = (tile - job.tile0) * job.rows_per_tile;
         const long long nrows = min(static_cast<long long>(job.rows_per_tile), job.rows - row0);
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
         mbar_arrive_expect_tx(&full_bar[s], bytes);  // release: desc visible to waiters
         bulk_g2s(smem_raw + static_cast<size_t>(s) * STAGE_BYTES, job.x + row0 * job.cols, bytes,
                  &full_bar[s]);
+        if (++s == kStages) { s = 0; ++round; }
       }
     }
     return;
@@ -168,11 +169,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
   const bool sym = b.symmetric != 0;
   const int bits = b.bits;
   const QRange qr = qrange(bits, sym);
-  long long it = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = static_cast<int>(it % kStages);
-    const uint32_t ph = static_cast<uint32_t>((it / kStages) & 1);
-    const int buf = static_cast<int>(it % 3);
+  int s = -1, buf = -1;
+  uint32_t ph = 1;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (++s == kStages) s = 0;
+    if (s == 0) ph ^= 1;
+    if (++buf == 3) buf = 0;
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * STAGE_BYTES);
 
     mbar_wait(&full_bar[s], ph);
@@ -188,7 +190,19 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
     // atomic per chunk merges the row statistics (no row-change bookkeeping).
     const unsigned magic = job.cpr_magic;  // row of chunk c = (c * magic) >> 20
+    const bool full_tile = nchunks == NW * kMaxChunksPerWarp;
+    const bool plain = sym && !given;
     float4 v[kMaxChunksPerWarp];
+    if (plain && full_tile) {  // branch-free common case
+#pragma unroll
+      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+        const int c = warp + j * NW;
+        v[j] = t4[c * 32 + lane];
+        const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
+        if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
+      }
+    } else
 #pragma unroll
     for (int j = 0; j < kMaxChunksPerWarp; ++j) {
       const int c = warp + j * NW;
@@ -256,10 +270,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     }
     // Buffer (it+2)%3 was last read during the previous tile, which every warp has
     // left (they all passed the barrier above); it is next written two tiles from now.
-    if (tid < kMaxRowsPerTile) acc_reset(s_acc[(buf + 2) % 3][tid]);
+    if (tid < kMaxRowsPerTile) acc_reset(s_acc[buf == 0 ? 2 : buf - 1][tid]);
 
     // ---- pass 2: quantise from registers + store
-    {
+    const bool all_fast = __all_sync(0xffffffffu, lane >= kMaxChunksPerWarp || mine.mode == kFastSym);
+    if (full_tile && all_fast && !(pp && bits != 4)) {
+      // Tight path: every row of the tile is symmetric / unclipped / in the divide
+      // window.  (scale, reciprocal) per chunk slot via one broadcast LDS.64.
+      if (lane < kMaxChunksPerWarp) s_by[warp][lane] = make_float2(mine.b, mine.y);
+      __syncwarp();
+      int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
+      uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
+#pragma unroll
+      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+        const float2 by = s_by[warp][j];
+        RowQ rq;
+        rq.b = by.x; rq.y = by.y;
+        const float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq),
+                    t2 = div_row(v[j].z, rq), t3 = div_row(v[j].w, rq);
+        if (ql) *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) = bytes4(rmagic(t0), rmagic(t1), rmagic(t2), rmagic(t3));
+        if (pl) {
+          const uint32_t h =
+              (nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3)) ^ 0x8888u) & 0xFFFFu;
+          const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
+          if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(pl + j * NW * (kChunk / 2)) = h | (o << 16);
+        }
+      }
+      __syncwarp();  // s_by[warp] is rewritten next tile
+    } else {
 #pragma unroll
       for (int j = 0; j < kMaxChunksPerWarp; ++j) {
         const int c = warp + j * NW;
