@@ -27,6 +27,12 @@ _D = _c.c_double
 SIGNATURES = {
     "aeqb_version": (_I, []),
     "aeqb_last_error": (_c.c_char_p, []),
+    "aeqb_launch_count": (_L, []),
+    "aeqb_host_requant_rows_batch_f32": (_I, [_P, _L, _I, _I]),
+    "aeqb_host_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I]),
+    "aeqb_host_alloc": (_P, [_c.c_size_t]),
+    "aeqb_host_free": (None, [_P]),
+    "aeqb_host_release": (None, []),
     "aeqb_requant_rows_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "aeqb_requant_given_minmax_f32":
         (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

@@ -14,6 +14,7 @@ from typing import Any, Optional
 
 import numpy as np
 
+from ... import host
 from ... import hostio
 from ... import qtyping
 from ..utils import common_utils
@@ -51,15 +52,29 @@ def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConf
     if qdim != tensor_content.ndim - 1:
       raise ValueError("blockwise quantisation cuts the last axis")
     uqt._blockwise_shape(shape, qdim, block)  # reference's divisibility error
-    x = hostio.to_device(tensor_content.reshape(-1, shape[-1]), np.float32)
-    out = device.requant_blocks(x, block, bits, clip=clip, want_scale_f16=False)
+    w2 = tensor_content.reshape(-1, shape[-1])
+    if clip is None:  # host-buffer pipeline: chunked H2D -> fused kernel -> D2H
+      q, _, scale, _ = host.requant_blocks([w2], block, bits)[0]
+      scale = scale.reshape(*shape[:-1], shape[-1] // block)
+      return qtyping.UniformQuantParams(
+          num_bits=bits, quantized_dimension=qdim, scale=scale,
+          zero_point=np.zeros(scale.shape, dtype=uqt.numpy_dtype_for(bits)), symmetric=sym,
+          quantized_data=q.reshape(shape), block_size=block)
+    out = device.requant_blocks(hostio.to_device(w2, np.float32), block, bits, clip=clip,
+                                want_scale_f16=False)
     scale = hostio.to_host(out.scale).reshape(*shape[:-1], shape[-1] // block)
     zp = np.zeros(scale.shape, dtype=uqt.numpy_dtype_for(bits))
   elif gran == _Gran.CHANNELWISE and qdim is not None:
-    x = hostio.to_device(_as_rows(tensor_content, qdim), np.float32)
-    out = device.requant_rows(x, bits, sym, clip=clip)
+    w2 = _as_rows(tensor_content, qdim)
     pshape = [1] * tensor_content.ndim
     pshape[qdim] = shape[qdim]
+    if clip is None:
+      q, _, scale, zp = host.requant_rows([w2], bits, sym)[0]
+      return qtyping.UniformQuantParams(
+          num_bits=bits, quantized_dimension=qdim, scale=scale.reshape(pshape),
+          zero_point=zp.reshape(pshape).astype(uqt.numpy_dtype_for(bits)), symmetric=sym,
+          quantized_data=q.reshape(shape), block_size=0)
+    out = device.requant_rows(hostio.to_device(w2, np.float32), bits, sym, clip=clip)
     scale = hostio.to_host(out.scale).reshape(pshape)
     zp = hostio.to_host(out.zero_point).reshape(pshape).astype(uqt.numpy_dtype_for(bits))
   elif gran in (_Gran.TENSORWISE, _Gran.CHANNELWISE):

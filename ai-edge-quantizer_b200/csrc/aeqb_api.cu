@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/aeqb200.h"
@@ -42,10 +43,24 @@ bool bits_ok(int bits) { return bits == 2 || bits == 4 || bits == 8; }
 
 }  // namespace
 
+namespace aeqb {
+std::atomic<long long> g_launches{0};
+int host_fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+int host_check(cudaError_t e, const char* what) { return check(e, what); }
+int sm_count_cached() { return sm_count(); }
+}  // namespace aeqb
+
 extern "C" {
 
 int aeqb_version(void) { return AEQB_VERSION; }
 const char* aeqb_last_error(void) { return g_err; }
+int64_t aeqb_launch_count(void) { return aeqb::g_launches.load(); }
 
 // ---- shared batching logic --------------------------------------------------
 namespace {

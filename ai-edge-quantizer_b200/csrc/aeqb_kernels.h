@@ -4,7 +4,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace aeqb {
+
+// Kernel launches issued by this library since load (aeqb_launch_count()).
+extern std::atomic<long long> g_launches;
+inline cudaError_t count_launch(int n = 1) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
 
 constexpr int kMaxInlineJobs = 64;
 

@@ -120,7 +120,7 @@ cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip,
   if (n <= 0) return cudaSuccess;
   scale_zp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
       mn, mx, clip, n, bits, symmetric, blockwise, scale, zp, scale_f16);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 cudaError_t launch_quantize(const float* x, long long n, long long channels, long long inner,
@@ -135,7 +135,7 @@ cudaError_t launch_quantize(const float* x, long long n, long long channels, lon
     quantize_kernel<int16_t><<<g, 256, 0, st>>>(x, n, channels, inner, scale, zp, pstride, qr.lo, qr.hi, static_cast<int16_t*>(q));
   else
     return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  return count_launch();
 }
 
 cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long channels,
@@ -151,7 +151,7 @@ cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long
     dequantize_kernel<int32_t><<<g, 256, 0, st>>>(static_cast<const int32_t*>(q), n, channels, inner, scale, zp, pstride, wrap8, out);
   else
     return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  return count_launch();
 }
 
 cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, int sm_count,
@@ -159,7 +159,7 @@ cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, in
   if (n <= 0) return cudaSuccess;
   const long long n_out = (n * bits + 7) / 8;
   pack_kernel<<<grid_for(n_out, sm_count), 256, 0, st>>>(q, n, bits, out, n_out);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 }  // namespace aeqb

@@ -194,7 +194,7 @@ cudaError_t launch_minmax_tensor(const float* x, long long n, float lo, float hi
         x, n, use_lo ? lo : -INFINITY, use_hi ? hi : INFINITY, ws);
   }
   minmax_tensor_final<<<1, 1, 0, st>>>(ws, use_lo, use_hi, n, out2);
-  return cudaGetLastError();
+  return count_launch(n > 0 ? 3 : 2);
 }
 
 cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn, float* mx,
@@ -203,7 +203,7 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
   const int warps = 8;
   const long long grid = (rows + warps - 1) / warps;
   row_stats_kernel<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(x, rows, cols, mn, mx, sumsq);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,
@@ -218,7 +218,7 @@ cudaError_t launch_block_minmax(const float* x, long long n, int block, float* m
     case 256: block_minmax_kernel<256><<<grid, 256, 0, st>>>(x, n, mn, mx); break;
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  return count_launch();
 }
 
 }  // namespace aeqb

@@ -247,7 +247,7 @@ cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
   long long grid = static_cast<long long>(sm_count) * 2;
   if (grid > b.n_tiles) grid = b.n_tiles;
   kern<<<static_cast<unsigned>(grid), (kNW + 1) * 32, smem, st>>>(b);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 template <int BLOCK>
@@ -288,7 +288,7 @@ cudaError_t launch_requant_blocks_generic(const BlocksJob& j, int block, int bit
   const long long n_blocks = j.n / block;
   const long long grid = (n_blocks + warps - 1) / warps;
   requant_blocks_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(j, block, bits);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 }  // namespace aeqb

@@ -414,7 +414,7 @@ cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cud
   long long grid = static_cast<long long>(sm_count) * ctas_per_sm;
   if (grid > b.n_tiles) grid = b.n_tiles;
   kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 }  // namespace
@@ -451,7 +451,7 @@ cudaError_t launch_requant_rows_generic(const RowsJob& j, int bits, int symmetri
   const int warps = 8;
   const long long grid = (j.rows + warps - 1) / warps;
   requant_rows_generic<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(j, bits, symmetric);
-  return cudaGetLastError();
+  return count_launch();
 }
 
 }  // namespace aeqb

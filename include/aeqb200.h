@@ -40,6 +40,8 @@ extern "C" {
 
 AEQB_API int aeqb_version(void);
 AEQB_API const char* aeqb_last_error(void);
+/* Number of CUDA kernels this library has launched since it was loaded. */
+AEQB_API int64_t aeqb_launch_count(void);
 
 /* ---------------------------------------------------------------- weights, fused
  * Per-channel min/max -> scale/zp -> quantise (-> pack) in one pass.
@@ -110,6 +112,24 @@ AEQB_API int aeqb_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jo
                                          int symmetric, void* stream);
 AEQB_API int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block,
                                            int bits, void* stream);
+
+/* ---------------------------------------------------------------- host buffers
+ * The call a NumPy caller makes (naive_min_max_quantize.get_tensor_quant_params,
+ * :34-110, over every weight of a model): HOST pointers in the job structs, in
+ * and out.  Tensors are cut into ~32 MiB row chunks and pipelined
+ * copy-in -> H2D -> fused kernel -> D2H -> copy-out over 4 slots / streams;
+ * page-locked ranges (aeqb_host_alloc, cudaHostRegister) are DMA'd in place,
+ * pageable ones are staged.  Returns when every output is in host memory.
+ * `clip` must be NULL here. */
+AEQB_API int aeqb_host_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
+                                              int symmetric);
+AEQB_API int aeqb_host_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs,
+                                                int block, int bits);
+/* Page-locked host memory for callers that want zero-copy staging. */
+AEQB_API void* aeqb_host_alloc(size_t bytes);
+AEQB_API void aeqb_host_free(void* p);
+/* Frees the pipeline's streams, device slots and pinned staging buffers. */
+AEQB_API void aeqb_host_release(void);
 
 /* ---------------------------------------------------------------- statistics
  * Whole-tensor min/max with the open-interval validity filter and raw fallback:
