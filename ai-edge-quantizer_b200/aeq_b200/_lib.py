@@ -43,6 +43,11 @@ SIGNATURES = {
     "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),
     "aeqb_row_stats_f32": (_I, [_P, _L, _L, _P, _P, _P, _P]),
     "aeqb_minmax_blocks_f32": (_I, [_P, _L, _L, _I, _P, _P, _P]),
+    "aeqb_octav_workspace_bytes": (_c.c_size_t, [_L, _I]),
+    "aeqb_octav_clip_rows_f32": (_I, [_P, _L, _L, _I, _I, _F, _I, _P, _P, _P]),
+    "aeqb_octav_clip_blocks_f32": (_I, [_P, _L, _L, _I, _I, _I, _F, _I, _P, _P, _P]),
+    "aeqb_mse_scale_rows_f32": (_I, [_P, _L, _L, _F, _P, _P]),
+    "aeqb_hadamard_rows_f32": (_I, [_P, _L, _L, _L, _P, _P]),
     "aeqb_scale_zp_from_minmax": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "aeqb_quantize_f32": (_I, [_P, _L, _L, _L, _P, _P, _I, _I, _I, _P, _P]),
     "aeqb_dequantize_f32": (_I, [_P, _I, _L, _L, _L, _P, _P, _I, _I, _P, _P]),

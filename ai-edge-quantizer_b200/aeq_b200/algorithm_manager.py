@@ -12,7 +12,10 @@ import functools
 
 from . import algorithm_manager_api
 from . import qtyping
+from .algorithms.uniform_quantize import hadamard_rotation
+from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
+from .algorithms.uniform_quantize import octav
 from .algorithms.utils import common_utils
 from .utils import qsv_utils
 
@@ -91,4 +94,15 @@ def register_weight_algorithm(algorithm_key, get_tensor_quant_params, calibratio
 
 register_weight_algorithm(AlgorithmName.MIN_MAX_UNIFORM_QUANT,
                           naive_min_max_quantize.get_tensor_quant_params,
+                          naive_min_max_quantize.min_max_calibrate)
+# OCTAV / MSE calibrate activations exactly like min-max (algorithm_manager.py:316-336, 446-466).
+register_weight_algorithm(AlgorithmName.OCTAV, octav.get_tensor_quant_params,
+                          naive_min_max_quantize.min_max_calibrate)
+register_weight_algorithm(AlgorithmName.MSE, mse.get_tensor_quant_params,
+                          naive_min_max_quantize.min_max_calibrate)
+# Weight-only rotation; the reference's own FC / EMBEDDING materialisers add the
+# activation-side INSERT_HADAMARD_ROTATION (hadamard_rotation.py:206-500) and are
+# reached through plugin.install.
+register_weight_algorithm(AlgorithmName.HADAMARD_ROTATION,
+                          hadamard_rotation.get_tensor_quant_params,
                           naive_min_max_quantize.min_max_calibrate)

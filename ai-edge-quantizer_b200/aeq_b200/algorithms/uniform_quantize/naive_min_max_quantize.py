@@ -36,8 +36,12 @@ def _as_rows(tensor_content: np.ndarray, quantized_dim):
 
 
 def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConfig,
-                    tensor_content: np.ndarray, clip=None) -> qtyping.UniformQuantParams:
-  """Fused min/max -> scale -> quantise of a constant tensor; `clip` is a device tensor."""
+                    tensor_content: np.ndarray, clip=None, x_dev=None) -> qtyping.UniformQuantParams:
+  """Fused min/max -> scale -> quantise of a constant tensor.
+
+  `clip` is a device tensor of clipping constants (OCTAV); `x_dev` an optional
+  device copy of `tensor_content` (same element order) that is already resident.
+  """
   from ... import device
   if tensor_content.dtype != np.float32:
     raise ValueError(f"only float32 weights are quantised, got {tensor_content.dtype}")
@@ -60,8 +64,8 @@ def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConf
           num_bits=bits, quantized_dimension=qdim, scale=scale,
           zero_point=np.zeros(scale.shape, dtype=uqt.numpy_dtype_for(bits)), symmetric=sym,
           quantized_data=q.reshape(shape), block_size=block)
-    out = device.requant_blocks(hostio.to_device(w2, np.float32), block, bits, clip=clip,
-                                want_scale_f16=False)
+    xd = hostio.to_device(w2, np.float32) if x_dev is None else x_dev.reshape(w2.shape)
+    out = device.requant_blocks(xd, block, bits, clip=clip, want_scale_f16=False)
     scale = hostio.to_host(out.scale).reshape(*shape[:-1], shape[-1] // block)
     zp = np.zeros(scale.shape, dtype=uqt.numpy_dtype_for(bits))
   elif gran == _Gran.CHANNELWISE and qdim is not None:
@@ -74,13 +78,15 @@ def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConf
           num_bits=bits, quantized_dimension=qdim, scale=scale.reshape(pshape),
           zero_point=zp.reshape(pshape).astype(uqt.numpy_dtype_for(bits)), symmetric=sym,
           quantized_data=q.reshape(shape), block_size=0)
-    out = device.requant_rows(hostio.to_device(w2, np.float32), bits, sym, clip=clip)
+    xd = hostio.to_device(w2, np.float32) if x_dev is None else x_dev.reshape(w2.shape)
+    out = device.requant_rows(xd, bits, sym, clip=clip)
     scale = hostio.to_host(out.scale).reshape(pshape)
     zp = hostio.to_host(out.zero_point).reshape(pshape).astype(uqt.numpy_dtype_for(bits))
   elif gran in (_Gran.TENSORWISE, _Gran.CHANNELWISE):
     # CHANNELWISE on an op without a quantised-dim entry reduces over everything,
     # like get_reduce_dims(None) -> axis=None in the reference.
-    x = hostio.to_device(tensor_content.reshape(1, -1), np.float32)
+    x = (hostio.to_device(tensor_content.reshape(1, -1), np.float32) if x_dev is None
+         else x_dev.reshape(1, -1))
     mm = device.minmax_tensor(x)
     out = device.requant_given_minmax(x, mm[0:1], mm[1:2], bits, sym, per_row=False, clip=clip)
     pshape = [1] * tensor_content.ndim

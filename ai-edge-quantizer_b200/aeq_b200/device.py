@@ -281,3 +281,59 @@ def requant_blocks_batch(xs, block: int, bits: int, want_q: bool = False,
   _lib.call("aeqb_requant_blocks_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), n, block, bits,
             _stream())
   return outs
+
+
+# ------------------------------------------------------------------ OCTAV / MSE / Hadamard
+def _octav_ws(groups: int, iters: int, dev: torch.device) -> torch.Tensor:
+  n = _lib.load().aeqb_octav_workspace_bytes(groups, iters)
+  return torch.empty(n, dtype=torch.uint8, device=dev)
+
+
+def octav_clip_rows(x: torch.Tensor, bits: int, max_iterations: int = 10,
+                    exponent_divisor: float = 3.0, early_stop: bool = True) -> torch.Tensor:
+  """OCTAV clipping constant per row, [rows, 1] (aeqb_octav_clip_rows_f32); a [1, n] view gives
+  the per-tensor constant."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  clip = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+  ws = _octav_ws(rows, max_iterations, x.device)
+  _lib.call("aeqb_octav_clip_rows_f32", _ptr(x), rows, cols, bits, max_iterations,
+            float(exponent_divisor), int(early_stop), _ptr(clip), _ptr(ws), _stream())
+  return clip
+
+
+def octav_clip_blocks(x: torch.Tensor, block: int, bits: int, max_iterations: int = 10,
+                      exponent_divisor: float = 3.0, early_stop: bool = True) -> torch.Tensor:
+  """OCTAV clipping constant per `block`-long group, [rows, cols/block]."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  if cols % block:
+    raise ValueError(
+        f"Quantized dimension {cols} in tensor shape {tuple(x.shape)} is not"
+        f" divisible by block size {block}.")
+  clip = torch.empty((rows, cols // block), dtype=torch.float32, device=x.device)
+  ws = _octav_ws(clip.numel(), max_iterations, x.device)
+  _lib.call("aeqb_octav_clip_blocks_f32", _ptr(x), rows, cols, block, bits, max_iterations,
+            float(exponent_divisor), int(early_stop), _ptr(clip), _ptr(ws), _stream())
+  return clip
+
+
+def mse_scale_rows(x: torch.Tensor, multiplier: float) -> torch.Tensor:
+  """multiplier * sqrt(mean(x^2)) per row, [rows, 1] (aeqb_mse_scale_rows_f32)."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  scale = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+  _lib.call("aeqb_mse_scale_rows_f32", _ptr(x), rows, cols, float(multiplier), _ptr(scale),
+            _stream())
+  return scale
+
+
+def hadamard_rows(x: torch.Tensor, hadamard_size: int, out: Optional[torch.Tensor] = None):
+  """x.reshape(-1, n) @ (H_n / sqrt(n)) along the last axis (aeqb_hadamard_rows_f32)."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  if out is None:
+    out = torch.empty_like(x)
+  _lib.call("aeqb_hadamard_rows_f32", _ptr(x), rows, cols, int(hadamard_size), _ptr(out),
+            _stream())
+  return out

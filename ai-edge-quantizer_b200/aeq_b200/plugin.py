@@ -18,7 +18,10 @@ from __future__ import annotations
 import functools
 
 from . import qtyping as _qt
+from .algorithms.uniform_quantize import hadamard_rotation
+from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
+from .algorithms.uniform_quantize import octav
 
 # algorithm key -> (attribute of the reference module holding {op: materialize_fn},
 #                   our get_tensor_quant_params, reference module attr that owns init/calibrate)
@@ -26,6 +29,18 @@ _BINDINGS = {
     "min_max_uniform_quantize": ("MIN_MAX_OP_NAME_MATERIALIZE_FUNC_DICT",
                                  naive_min_max_quantize.get_tensor_quant_params,
                                  "naive_min_max_quantize"),
+    "OCTAV": ("_OCTAV_OP_NAME_MATERIALIZE_FUNC_DICT", octav.get_tensor_quant_params,
+              "naive_min_max_quantize"),
+    "MSE": ("_MSE_OP_NAME_MATERIALIZE_FUNC_DICT", mse.get_tensor_quant_params,
+            "naive_min_max_quantize"),
+}
+
+# Algorithms whose reference materialisers call their module's own
+# `get_tensor_quant_params` global at call time instead of receiving it through
+# functools.partial (hadamard_rotation.py:253, :423): the seam is that attribute.
+_MODULE_SEAMS = {
+    "HADAMARD_ROTATION": ("hadamard_rotation", hadamard_rotation.get_tensor_quant_params),
+    "DECOMPOSED_HADAMARD_ROTATION": ("hadamard_rotation", hadamard_rotation.get_tensor_quant_params),
 }
 
 
@@ -69,6 +84,16 @@ def _adapt(fn, ref_qtyping):
   return get_tensor_quant_params
 
 
+_saved: list = []  # undo log of install(): (callable, args) pairs, replayed in reverse
+
+
+def uninstall() -> None:
+  """Restores every registration / module attribute `install` replaced."""
+  while _saved:
+    fn, args = _saved.pop()
+    fn(*args)
+
+
 def install(reference_algorithm_manager, algorithms=None) -> list[str]:
   """Re-registers the reference's ops with device-backed arithmetic; returns the keys bound."""
   am = reference_algorithm_manager
@@ -84,10 +109,27 @@ def install(reference_algorithm_manager, algorithms=None) -> list[str]:
     adapted = _adapt(fn, ref_qtyping)
     for op_name, materialize_func in op_dict.items():
       inner = materialize_func.func if isinstance(materialize_func, functools.partial) else materialize_func
+      _saved.append((am.register_quantized_op, (
+          key, op_name, am.get_init_qsv_func(key, op_name),
+          am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE),
+          am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.MATERIALIZE),
+          am.get_update_qsv_func(key, op_name))))
       am.register_quantized_op(
           key, op_name, mod.init_qsvs,
           calibration_func=am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE),
           materialize_func=functools.partial(inner, adapted),
           update_qsv_func=am.get_update_qsv_func(key, op_name))
+    bound.append(key)
+  for key, (ref_module, fn) in _MODULE_SEAMS.items():
+    if algorithms is not None and key not in algorithms:
+      continue
+    mod = getattr(am, ref_module, None)
+    if mod is None:
+      continue
+    if not getattr(mod.get_tensor_quant_params, "_aeqb200", False):
+      adapted = _adapt(fn, ref_qtyping)
+      adapted._aeqb200 = True
+      _saved.append((setattr, (mod, "get_tensor_quant_params", mod.get_tensor_quant_params)))
+      mod.get_tensor_quant_params = adapted
     bound.append(key)
   return bound

@@ -258,6 +258,60 @@ int aeqb_minmax_blocks_f32(const float* x, int64_t rows, int64_t cols, int block
                "aeqb_minmax_blocks_f32");
 }
 
+size_t aeqb_octav_workspace_bytes(int64_t groups, int max_iterations) {
+  if (groups < 0 || max_iterations < 1) return 0;
+  return aeqb::octav_workspace_bytes(groups, max_iterations);
+}
+
+int aeqb_octav_clip_rows_f32(const float* x, int64_t rows, int64_t cols, int bits,
+                             int max_iterations, float exponent_divisor, int early_stop,
+                             float* clip, void* ws, void* stream) {
+  if (rows < 0 || cols < 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+  if (bits < 1 || bits > 16) return fail("unsupported num_bits %d", bits);
+  if (max_iterations < 1 || max_iterations > 32) return fail("max_iterations must be in [1, 32]");
+  if (rows * cols > 0 && (!x || !clip || !ws)) return fail("x / clip / ws are NULL");
+  return check(aeqb::launch_octav_rows(x, rows, cols, bits, max_iterations, exponent_divisor,
+                                       early_stop, clip, ws, sm_count(),
+                                       static_cast<cudaStream_t>(stream)),
+               "aeqb_octav_clip_rows_f32");
+}
+
+int aeqb_octav_clip_blocks_f32(const float* x, int64_t rows, int64_t cols, int block, int bits,
+                               int max_iterations, float exponent_divisor, int early_stop,
+                               float* clip, void* ws, void* stream) {
+  if (rows < 0 || cols < 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+  if (block != 32 && block != 64 && block != 128 && block != 256) return fail("unsupported block size %d", block);
+  if (cols % block)
+    return fail("Quantized dimension %lld is not divisible by block size %d.", (long long)cols, block);
+  if (bits < 1 || bits > 16) return fail("unsupported num_bits %d", bits);
+  if (max_iterations < 1 || max_iterations > 32) return fail("max_iterations must be in [1, 32]");
+  if (rows * cols > 0 && (!x || !clip || !ws)) return fail("x / clip / ws are NULL");
+  return check(aeqb::launch_octav_blocks(x, rows * cols, block, bits, max_iterations,
+                                         exponent_divisor, early_stop, clip, ws, sm_count(),
+                                         static_cast<cudaStream_t>(stream)),
+               "aeqb_octav_clip_blocks_f32");
+}
+
+int aeqb_mse_scale_rows_f32(const float* x, int64_t rows, int64_t cols, float k, float* scale,
+                            void* stream) {
+  if (rows < 0 || cols <= 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+  if (rows > 0 && (!x || !scale)) return fail("x / scale are NULL");
+  return check(aeqb::launch_mse_scale_rows(x, rows, cols, k, scale, sm_count(),
+                                           static_cast<cudaStream_t>(stream)),
+               "aeqb_mse_scale_rows_f32");
+}
+
+int aeqb_hadamard_rows_f32(const float* x, int64_t rows, int64_t cols, int64_t n, float* out,
+                           void* stream) {
+  if (rows < 0 || cols < 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+  if (n < 2 || (n & (n - 1))) return fail("Hadamard matrix size must be a power of 2. ");
+  if (cols % n) return fail("hadamard size %lld does not divide the last dimension %lld", (long long)n, (long long)cols);
+  if (rows * cols > 0 && (!x || !out)) return fail("x / out are NULL");
+  return check(aeqb::launch_hadamard_rows(x, rows, cols, n, out, sm_count(),
+                                          static_cast<cudaStream_t>(stream)),
+               "aeqb_hadamard_rows_f32");
+}
+
 int aeqb_scale_zp_from_minmax(const float* mn, const float* mx, const float* clip, int64_t n,
                               int bits, int symmetric, int blockwise, float* scale, int32_t* zp,
                               uint16_t* scale_f16, void* stream) {

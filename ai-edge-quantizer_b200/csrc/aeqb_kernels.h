@@ -2,6 +2,7 @@
 // Not installed; the public boundary is include/aeqb200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -85,6 +86,22 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
                              float* sumsq, cudaStream_t st);
 cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,
                                 cudaStream_t st);
+
+cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols, float k,
+                                  float* scale, int sm_count, cudaStream_t st);
+
+// OCTAV clipping search (octav.cu).  ws: octav_workspace_bytes(groups, iters) bytes.
+size_t octav_workspace_bytes(long long groups, int iters);
+cudaError_t launch_octav_rows(const float* x, long long rows, long long cols, int bits, int iters,
+                              float divisor, int early_stop, float* clip, void* ws, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_octav_blocks(const float* x, long long n, int block, int bits, int iters,
+                                float divisor, int early_stop, float* clip, void* ws, int sm_count,
+                                cudaStream_t st);
+
+// Block-diagonal Hadamard rotation of the last axis (hadamard.cu).
+cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols, long long n,
+                                 float* out, int sm_count, cudaStream_t st);
 
 // Unfused element-wise pieces (elementwise.cu).
 cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,

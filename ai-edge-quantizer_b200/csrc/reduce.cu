@@ -143,6 +143,46 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- MSE scale
+// mse.get_tensor_quant_params (mse.py:100-108): scale = k * sqrt(mean(x**2)) per row
+// (rows == 1: per tensor).  x**2 is rounded to fp32 like the reference's temporary;
+// the sum runs in fp64 and is rounded once (NumPy's pairwise fp32 sum is within a
+// few ulp of that), then fp32 divide, sqrt and multiply as NumPy does.
+__global__ void __launch_bounds__(1024)
+    mse_scale_rows_kernel(const float* __restrict__ x, long long rows, long long cols, float k,
+                          float* __restrict__ scale) {
+  __shared__ double s_part[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* p = x + row * cols;
+    double acc = 0.0;
+    if ((reinterpret_cast<uintptr_t>(p) % 16 == 0) && (cols % 4 == 0)) {
+      const float4* pv = reinterpret_cast<const float4*>(p);
+      for (long long i = tid; i < cols / 4; i += blockDim.x) {
+        const float4 v = ldg_stream(pv + i);
+        acc += static_cast<double>(__fmul_rn(v.x, v.x)) + static_cast<double>(__fmul_rn(v.y, v.y));
+        acc += static_cast<double>(__fmul_rn(v.z, v.z)) + static_cast<double>(__fmul_rn(v.w, v.w));
+      }
+    } else {
+      for (long long i = tid; i < cols; i += blockDim.x) {
+        const float v = p[i];
+        acc += static_cast<double>(__fmul_rn(v, v));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < nw; ++w) t += s_part[w];
+      const float mean = __fdiv_rn(static_cast<float>(t), static_cast<float>(cols));
+      scale[row] = __fmul_rn(k, __fsqrt_rn(mean));
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- per block
 // block/8 lanes share a block; each lane owns 8 consecutive floats.
 template <int BLOCK>
@@ -203,6 +243,16 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
   const int warps = 8;
   const long long grid = (rows + warps - 1) / warps;
   row_stats_kernel<<<static_cast<unsigned>(grid), warps * 32, 0, st>>>(x, rows, cols, mn, mx, sumsq);
+  return count_launch();
+}
+
+cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols, float k,
+                                  float* scale, int sm_count, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int threads = cols >= 16384 ? 1024 : 256;
+  long long grid = static_cast<long long>(sm_count) * (threads == 1024 ? 2 : 8);
+  if (grid > rows) grid = rows;
+  mse_scale_rows_kernel<<<static_cast<unsigned>(grid), threads, 0, st>>>(x, rows, cols, k, scale);
   return count_launch();
 }
 

@@ -154,6 +154,36 @@ AEQB_API int aeqb_row_stats_f32(const float* x, int64_t rows, int64_t cols, floa
 AEQB_API int aeqb_minmax_blocks_f32(const float* x, int64_t rows, int64_t cols, int block,
                                     float* mn, float* mx, void* stream);
 
+/* ---------------------------------------------------------------- OCTAV / MSE / Hadamard
+ * OCTAV clipping constants, octav._guess_clipping_with_octav
+ * (algorithms/uniform_quantize/octav.py:30-112): Newton iterations of eq. (6) from
+ * c = 1 with the reference's GLOBAL np.allclose early stop.  One HBM pass computes
+ * every group's whole trajectory; a select step picks the iteration the reference
+ * stops at.  rows variant: one constant per row (rows == 1: per tensor);
+ * blocks variant: one per `block`-long group, clip shaped [rows, cols/block].
+ *   exponent_divisor: 3.0 (signed), max_iterations: 10 in octav.py:186-192.
+ *   ws: aeqb_octav_workspace_bytes(number of constants, max_iterations) bytes. */
+AEQB_API size_t aeqb_octav_workspace_bytes(int64_t groups, int max_iterations);
+AEQB_API int aeqb_octav_clip_rows_f32(const float* x, int64_t rows, int64_t cols, int bits,
+                                      int max_iterations, float exponent_divisor, int early_stop,
+                                      float* clip, void* ws, void* stream);
+AEQB_API int aeqb_octav_clip_blocks_f32(const float* x, int64_t rows, int64_t cols, int block,
+                                        int bits, int max_iterations, float exponent_divisor,
+                                        int early_stop, float* clip, void* ws, void* stream);
+
+/* scale[r] = k * sqrt(mean(x[r, :]^2)), mse.get_tensor_quant_params
+ * (algorithms/uniform_quantize/mse.py:100-108); rows == 1 gives the per-tensor scale. */
+AEQB_API int aeqb_mse_scale_rows_f32(const float* x, int64_t rows, int64_t cols, float k,
+                                     float* scale, void* stream);
+
+/* out = x.reshape(-1, n) @ (H_n / sqrt(n)) over the last axis,
+ * hadamard_rotation._rotate_with_diagonal_hadamard
+ * (algorithms/uniform_quantize/hadamard_rotation.py:93-134).  n: power of two
+ * dividing cols (the caller applies gcd / max_hadamard_size, :121-123).
+ * out may alias x. */
+AEQB_API int aeqb_hadamard_rows_f32(const float* x, int64_t rows, int64_t cols, int64_t n,
+                                    float* out, void* stream);
+
 /* ---------------------------------------------------------------- unfused pieces
  * tensor_zp_scale_from_min_max (uqt:492-586) on n (min, max[, clip]) triples.
  * blockwise != 0 applies the bf16->fp16 scale rounding (uqt:577-581) and, with

@@ -199,13 +199,23 @@ def test_plugin_installs_into_reference_registry():
     pytest.skip("reference tree not mounted")
   from aeq_b200 import plugin
   ram = refshim.ref("algorithm_manager")
-  bound = plugin.install(ram)
-  assert "min_max_uniform_quantize" in bound
   rq = ram.qtyping
-  f = ram.get_quantization_func("min_max_uniform_quantize", rq.TFLOperationName.FULLY_CONNECTED,
+  ref_had = ram.hadamard_rotation.get_tensor_quant_params
+  bound = plugin.install(ram)
+  try:
+    assert {"min_max_uniform_quantize", "OCTAV", "MSE", "HADAMARD_ROTATION"} <= set(bound)
+    for key in ("min_max_uniform_quantize", "OCTAV", "MSE"):
+      f = ram.get_quantization_func(key, rq.TFLOperationName.FULLY_CONNECTED,
+                                    rq.QuantizeMode.MATERIALIZE)
+      assert f.func.__name__ == "materialize_fc_conv"
+      assert f.args[0].__module__.startswith("aeq_b200.")
+    f = ram.get_quantization_func("min_max_uniform_quantize", rq.TFLOperationName.TRANSPOSE,
+                                  rq.QuantizeMode.MATERIALIZE)
+    assert f.func.__name__ == "materialize_transpose"
+    assert ram.hadamard_rotation.get_tensor_quant_params is not ref_had
+  finally:
+    plugin.uninstall()
+  f = ram.get_quantization_func("OCTAV", rq.TFLOperationName.FULLY_CONNECTED,
                                 rq.QuantizeMode.MATERIALIZE)
-  assert f.func.__name__ == "materialize_fc_conv"
-  assert f.args[0].__module__.startswith("aeq_b200.")
-  f = ram.get_quantization_func("min_max_uniform_quantize", rq.TFLOperationName.TRANSPOSE,
-                                rq.QuantizeMode.MATERIALIZE)
-  assert f.func.__name__ == "materialize_transpose"
+  assert f.args[0].__module__.startswith("ai_edge_quantizer.")
+  assert ram.hadamard_rotation.get_tensor_quant_params is ref_had
