@@ -12,6 +12,7 @@ import functools
 
 from . import algorithm_manager_api
 from . import qtyping
+from .algorithms.uniform_quantize import gptq
 from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
@@ -106,3 +107,12 @@ register_weight_algorithm(AlgorithmName.MSE, mse.get_tensor_quant_params,
 register_weight_algorithm(AlgorithmName.HADAMARD_ROTATION,
                           hadamard_rotation.get_tensor_quant_params,
                           naive_min_max_quantize.min_max_calibrate)
+# GPTQ: FULLY_CONNECTED only in the reference (algorithm_manager.py:434-455); the activation
+# QSV carries the Hessian and merges by sample-weighted mean.
+register_quantized_op(
+    AlgorithmName.GPTQ, _Op.FULLY_CONNECTED, _init_qsvs, calibration_func=gptq.calibrate,
+    materialize_func=functools.partial(common_utils.materialize_weight_op,
+                                       gptq.get_tensor_quant_params, inputs_to_ignore=()),
+    update_qsv_func=qsv_utils.gptq_and_moving_average_update)
+register_op_quant_config_validation_func(AlgorithmName.GPTQ, _check_config)
+register_config_check_policy_func(AlgorithmName.GPTQ, None)

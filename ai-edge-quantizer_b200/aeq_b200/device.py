@@ -337,3 +337,80 @@ def hadamard_rows(x: torch.Tensor, hadamard_size: int, out: Optional[torch.Tenso
   _lib.call("aeqb_hadamard_rows_f32", _ptr(x), rows, cols, int(hadamard_size), _ptr(out),
             _stream())
   return out
+
+
+# ------------------------------------------------------------------ GPTQ
+def xtx(x: torch.Tensor, alpha: float) -> torch.Tensor:
+  """float64 [K, K] = alpha * X^T X with fp32 accumulation, X = x.reshape(-1, K) (aeqb_xtx_f32)."""
+  if not x.is_cuda or x.dtype != torch.float32:
+    raise ValueError("expected a float32 CUDA tensor")
+  x2 = x.contiguous().reshape(-1, x.shape[-1])
+  tokens, k = x2.shape
+  h = torch.empty((k, k), dtype=torch.float64, device=x.device)
+  n = _lib.load().aeqb_xtx_workspace_bytes(tokens, k)
+  ws = torch.empty(n, dtype=torch.uint8, device=x.device) if n else None
+  _lib.call("aeqb_xtx_f32", _ptr(x2), tokens, k, float(alpha), _ptr(h), _ptr(ws), _stream())
+  return h
+
+
+def hessian_inverse(hessian: torch.Tensor, damp: float = 0.01,
+                    keep_damped_diagonal: bool = False) -> torch.Tensor:
+  """float32 inverse of the damped float64 Hessian (aeqb_hessian_inverse_f64).
+
+  Raises numpy.linalg.LinAlgError like np.linalg.cholesky when the damped matrix is not
+  positive definite (this reads one int back, i.e. synchronises)."""
+  import numpy as np
+  if not hessian.is_cuda or hessian.dtype != torch.float64 or hessian.dim() != 2:
+    raise ValueError("expected a float64 CUDA matrix")
+  if not hessian.is_contiguous():
+    raise ValueError("the Hessian must be contiguous (its diagonal may be updated in place)")
+  k = hessian.shape[0]
+  hinv = torch.empty((k, k), dtype=torch.float32, device=hessian.device)
+  ws = torch.empty(_lib.load().aeqb_hessian_inverse_workspace_bytes(k), dtype=torch.uint8,
+                   device=hessian.device)
+  info = torch.zeros(1, dtype=torch.int32, device=hessian.device)
+  _lib.call("aeqb_hessian_inverse_f64", _ptr(hessian), k, float(damp), int(keep_damped_diagonal),
+            _ptr(hinv), _ptr(ws), _ptr(info), _stream())
+  if int(info.item()) != 0:
+    raise np.linalg.LinAlgError("Matrix is not positive definite")
+  return hinv
+
+
+def gptq_quantize(w: torch.Tensor, hinv: torch.Tensor, scale: torch.Tensor,
+                  zp: Optional[torch.Tensor], block: int, bits: int, symmetric: bool) -> torch.Tensor:
+  """int8 [rows, k]: the 64-column lazy-block OBS loop (aeqb_gptq_quantize_f32); `w` is not modified."""
+  _check_f32_2d(w)
+  rows, k = w.shape
+  if hinv.shape != (k, k) or hinv.dtype != torch.float32 or not hinv.is_contiguous():
+    raise ValueError("hinv must be a contiguous float32 [k, k] matrix")
+  scale = scale.contiguous().float()
+  if block:
+    if scale.numel() != rows * (k // block):
+      raise ValueError("blockwise scales must be [rows, k / block]")
+    cols = k // block
+  elif scale.numel() == 1:
+    cols = 0
+  elif scale.numel() == rows:
+    cols = 1
+  else:
+    raise ValueError(f"scale holds {scale.numel()} values, expected 1 or {rows}")
+  if zp is not None:
+    zp = zp.to(torch.int32).contiguous()
+    if zp.numel() != scale.numel():
+      raise ValueError("zero_point must have the shape of scale")
+  work = w.clone()
+  q = torch.empty((rows, k), dtype=torch.int8, device=w.device)
+  _lib.call("aeqb_gptq_quantize_f32", _ptr(work), rows, k, _ptr(hinv), _ptr(scale), _ptr(zp), cols,
+            block, bits, int(symmetric), 64, _ptr(q), _stream())
+  return q
+
+
+def hessian_merge(a: torch.Tensor, wa: float, b: torch.Tensor, wb: float) -> torch.Tensor:
+  """(a * wa + b * wb) / (wa + wb) in float64 (aeqb_hessian_merge_f64)."""
+  if a.shape != b.shape or a.dtype != torch.float64 or b.dtype != torch.float64:
+    raise ValueError("expected two float64 tensors of one shape")
+  a, b = a.contiguous(), b.contiguous()
+  out = torch.empty_like(a)
+  _lib.call("aeqb_hessian_merge_f64", _ptr(a), float(wa), _ptr(b), float(wb), _ptr(out), a.numel(),
+            _stream())
+  return out

@@ -18,6 +18,7 @@ from __future__ import annotations
 import functools
 
 from . import qtyping as _qt
+from .algorithms.uniform_quantize import gptq
 from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
@@ -33,6 +34,8 @@ _BINDINGS = {
               "naive_min_max_quantize"),
     "MSE": ("_MSE_OP_NAME_MATERIALIZE_FUNC_DICT", mse.get_tensor_quant_params,
             "naive_min_max_quantize"),
+    "GPTQ": ("_GPTQ_OP_NAME_MATERIALIZE_FUNC_DICT", gptq.get_tensor_quant_params,
+             "naive_min_max_quantize"),
 }
 
 # Algorithms whose reference materialisers call their module's own

@@ -44,6 +44,20 @@ def gptq_and_moving_average_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV) -> qt
   if total == 0:
     out["hessian"], out["num_samples"] = new_qsv["hessian"], 0
   else:
-    out["hessian"] = (qsv["hessian"] * n_old + new_qsv["hessian"] * n_new) / total
+    out["hessian"] = _merge_hessian(qsv["hessian"], n_old, new_qsv["hessian"], n_new, total)
     out["num_samples"] = total
   return out
+
+
+def _merge_hessian(h_old, n_old, h_new, n_new, total):
+  """(H_old * n_old + H_new * n_new) / total in float64 on the device (aeqb_hessian_merge_f64).
+
+  NumPy in -> NumPy out; if either side is a device tensor the result stays on the device."""
+  del total
+  import torch
+  from .. import device, hostio
+  keep = isinstance(h_old, torch.Tensor) or isinstance(h_new, torch.Tensor)
+  a = h_old if isinstance(h_old, torch.Tensor) else hostio.to_device(np.asarray(h_old, np.float64))
+  b = h_new if isinstance(h_new, torch.Tensor) else hostio.to_device(np.asarray(h_new, np.float64))
+  out = device.hessian_merge(a.double(), float(n_old), b.double(), float(n_new))
+  return out if keep else hostio.to_host(out)

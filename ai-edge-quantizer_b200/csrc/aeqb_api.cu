@@ -312,6 +312,61 @@ int aeqb_hadamard_rows_f32(const float* x, int64_t rows, int64_t cols, int64_t n
                "aeqb_hadamard_rows_f32");
 }
 
+size_t aeqb_xtx_workspace_bytes(int64_t tokens, int64_t k) {
+  return aeqb::xtx_workspace_bytes(tokens, k, sm_count());
+}
+
+int aeqb_xtx_f32(const float* x, int64_t tokens, int64_t k, double alpha, double* hessian, void* ws,
+                 void* stream) {
+  if (tokens < 0 || k < 0 || k > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)tokens, (long long)k);
+  if (k > 0 && !hessian) return fail("hessian is NULL");
+  if (tokens * k > 0 && !x) return fail("x is NULL");
+  return check(aeqb::launch_xtx_f64(x, tokens, k, alpha, hessian, ws, sm_count(),
+                                    static_cast<cudaStream_t>(stream)),
+               "aeqb_xtx_f32");
+}
+
+size_t aeqb_hessian_inverse_workspace_bytes(int64_t k) {
+  return k > 0 ? aeqb::hessian_inverse_workspace_bytes(k) : 0;
+}
+
+int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp, int keep_damped_diagonal,
+                             float* hinv, void* ws, int* info, void* stream) {
+  if (k < 0 || k > 0x7fffffff) return fail("bad Hessian order %lld", (long long)k);
+  if (k > 0 && (!hessian || !hinv || !ws)) return fail("hessian / hinv / ws are NULL");
+  return check(aeqb::launch_hessian_inverse(hessian, k, damp, keep_damped_diagonal, hinv, ws, info,
+                                            sm_count(), static_cast<cudaStream_t>(stream)),
+               "aeqb_hessian_inverse_f64");
+}
+
+int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
+                           const float* scale, const int32_t* zp, int64_t scale_cols, int block,
+                           int bits, int symmetric, int blocksize, int8_t* q, void* stream) {
+  if (rows < 0 || k < 0 || rows > 0x7fffffff || k > 0x7fffffff)
+    return fail("bad shape [%lld, %lld]", (long long)rows, (long long)k);
+  if (blocksize != 64) return fail("GPTQ blocksize must be 64 (gptq.py:136), got %d", blocksize);
+  if (bits < 2 || bits > 8) return fail("unsupported num_bits %d (2..8)", bits);
+  if (block != 0 && block != 32 && block != 64 && block != 128 && block != 256)
+    return fail("unsupported block size %d", block);
+  if (block && (k % block || scale_cols != k / block))
+    return fail("blockwise scales must be [rows, k / block]");
+  if (!block && scale_cols != 0 && scale_cols != 1) return fail("scale_cols must be 0 or 1 without blocks");
+  if (rows * k > 0 && (!w_work || !hinv || !scale || !q)) return fail("w_work / hinv / scale / q are NULL");
+  return check(aeqb::launch_gptq_quantize(w_work, rows, k, hinv, scale, zp,
+                                          static_cast<int>(scale_cols), block, bits,
+                                          symmetric ? 1 : 0, q, static_cast<cudaStream_t>(stream)),
+               "aeqb_gptq_quantize_f32");
+}
+
+int aeqb_hessian_merge_f64(const double* a, double wa, const double* b, double wb, double* out,
+                           int64_t n, void* stream) {
+  if (n < 0) return fail("negative element count");
+  if (n > 0 && (!a || !b || !out)) return fail("a / b / out are NULL");
+  return check(aeqb::launch_weighted_mean_f64(a, wa, b, wb, out, n, sm_count(),
+                                              static_cast<cudaStream_t>(stream)),
+               "aeqb_hessian_merge_f64");
+}
+
 int aeqb_scale_zp_from_minmax(const float* mn, const float* mx, const float* clip, int64_t n,
                               int bits, int symmetric, int blockwise, float* scale, int32_t* zp,
                               uint16_t* scale_f16, void* stream) {

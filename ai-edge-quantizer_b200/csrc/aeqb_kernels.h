@@ -103,6 +103,22 @@ cudaError_t launch_octav_blocks(const float* x, long long n, int block, int bits
 cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols, long long n,
                                  float* out, int sm_count, cudaStream_t st);
 
+// GPTQ (gptq_hessian.cu, gptq_quantize.cu).
+size_t xtx_workspace_bytes(long long T, long long K, int sm_count);
+cudaError_t launch_xtx_f64(const float* x, long long T, long long K, double alpha, double* out,
+                           void* ws, int sm_count, cudaStream_t st);
+cudaError_t launch_xtx_f32(const float* x, long long T, long long K, double alpha, float* out,
+                           void* ws, int sm_count, cudaStream_t st);
+size_t hessian_inverse_workspace_bytes(long long K);
+cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, int mutate_diagonal,
+                                   float* hinv, void* ws, int* info_out, int sm_count,
+                                   cudaStream_t st);
+cudaError_t launch_weighted_mean_f64(const double* a, double wa, const double* b, double wb,
+                                     double* out, long long n, int sm_count, cudaStream_t st);
+cudaError_t launch_gptq_quantize(float* w_work, long long R, long long K, const float* hinv,
+                                 const float* scale, const int32_t* zp, int row_stride, int qblock,
+                                 int bits, int symmetric, int8_t* q, cudaStream_t st);
+
 // Unfused element-wise pieces (elementwise.cu).
 cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,
                             int bits, int symmetric, int blockwise, float* scale, int32_t* zp,

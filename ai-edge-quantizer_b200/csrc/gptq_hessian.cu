@@ -1,0 +1,533 @@
+// GPTQ, Hessian side — replaces
+//   gptq.calibrate's   H = (2 / num_samples) * X^T X          (algorithms/uniform_quantize/gptq.py:100-106)
+//   gptq._prepare_hessian_inverse                              (gptq.py:111-128)
+//     diag 0 -> 1, + damp * mean(diag); L = cholesky(H) in float64 (np.linalg.cholesky);
+//     L^-1 in float32 (scipy.linalg.lapack.strtri casts to single);
+//     H^-1 = einsum("ji,jk->ik", L^-1, L^-1) in float32
+//   qsv_utils._gptq_merge_hessian's weighted mean               (utils/qsv_utils.py:71-88)
+//
+// dtype flow mirrors NumPy 2: the GEMM accumulates in fp32 (X is
+// fp32, `x.T.dot(x)` is sgemm) and the float64 scalar 2/num_samples promotes the
+// product, so H is float64 holding fp32-rounded sums.
+//
+// Kernels (SIMT; the tensor-core version of the two dense contractions is the
+// next step):
+//   xtx_tile      128x128 output tile per CTA, 16-deep k-slabs of X staged in shared
+//                 memory, 8x8 register tile per thread, upper-triangular tiles only,
+//                 optional deterministic split over tokens (fixed-order reduce).
+//   chol_panel / chol_syrk   right-looking blocked Cholesky in fp64, block 32.
+//   trtri_diag / trtri_cols  blocked lower-triangular inverse in fp32, block 64.
+#include "aeqb_common.cuh"
+#include "aeqb_kernels.h"
+
+namespace aeqb {
+
+namespace {
+
+// ------------------------------------------------------------------ X^T X
+constexpr int XT = 128;  // output tile edge
+constexpr int XK = 16;   // tokens per slab
+
+// Upper-triangular tile index -> (bi, bj), bi <= bj.
+__device__ __forceinline__ void tri_index(int t, int nb, int& bi, int& bj) {
+  int row = 0, left = t;
+  while (left >= nb - row) {
+    left -= nb - row;
+    ++row;
+  }
+  bi = row;
+  bj = row + left;
+}
+
+// part != nullptr: raw fp32 partial sums for split `blockIdx.y` go to part[split][K][K]
+// (upper tiles only); otherwise out = alpha * sum written to both triangles.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+    xtx_tile(const float* __restrict__ X, long long T, int K, double alpha, OutT* __restrict__ out,
+             float* __restrict__ part, long long t_per_split) {
+  __shared__ __align__(16) float As[2][XK][XT];
+  __shared__ __align__(16) float Bs[2][XK][XT];
+  const int nb = (K + XT - 1) / XT;
+  int bi, bj;
+  tri_index(blockIdx.x, nb, bi, bj);
+  const int i0 = bi * XT, j0 = bj * XT;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 8 x 8 outputs (2 x 4 + 2 x 4)
+  const long long t_begin = static_cast<long long>(blockIdx.y) * t_per_split;
+  long long t_end = t_begin + t_per_split;
+  if (t_end > T) t_end = T;
+  const bool vec = (K % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0);
+
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+
+  // each thread stages two float4 of A and two of B per slab: slab row = (tid*2+u)/32, col4 = (tid*2+u)%32
+  auto load_slab = [&](int buf, long long t0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid * 2 + u;
+      const int r = idx >> 5, c4 = (idx & 31) * 4;
+      const long long t = t0 + r;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (t < t_end) {
+        const float* row = X + t * K;
+        if (vec) {
+          if (i0 + c4 < K) a = __ldg(reinterpret_cast<const float4*>(row + i0 + c4));
+          if (j0 + c4 < K) b = __ldg(reinterpret_cast<const float4*>(row + j0 + c4));
+        } else {
+          float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (i0 + c4 + e < K) ta[e] = row[i0 + c4 + e];
+            if (j0 + c4 + e < K) tb[e] = row[j0 + c4 + e];
+          }
+          a = make_float4(ta[0], ta[1], ta[2], ta[3]);
+          b = make_float4(tb[0], tb[1], tb[2], tb[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(&As[buf][r][c4]) = a;
+      *reinterpret_cast<float4*>(&Bs[buf][r][c4]) = b;
+    }
+  };
+
+  int buf = 0;
+  if (t_begin < t_end) load_slab(0, t_begin);
+  __syncthreads();
+  for (long long t0 = t_begin; t0 < t_end; t0 += XK) {
+    if (t0 + XK < t_end) load_slab(buf ^ 1, t0 + XK);
+#pragma unroll
+    for (int k = 0; k < XK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4 + 64]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4 + 64]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + ty * 4 + (a & 3) + (a >> 2) * 64;
+    if (i >= K) continue;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = j0 + tx * 4 + (b & 3) + (b >> 2) * 64;
+      if (j >= K) continue;
+      if (part) {
+        part[(static_cast<long long>(blockIdx.y) * K + i) * K + j] = acc[a][b];
+      } else {
+        const OutT v = static_cast<OutT>(alpha * static_cast<double>(acc[a][b]));
+        out[static_cast<long long>(i) * K + j] = v;
+        if (bi != bj) out[static_cast<long long>(j) * K + i] = v;
+      }
+    }
+  }
+}
+
+// Fixed-order sum of the token splits (deterministic), then alpha, both triangles.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+    xtx_reduce(const float* __restrict__ part, int splits, int K, double alpha, OutT* __restrict__ out) {
+  const long long n = static_cast<long long>(K) * K;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e / K), j = static_cast<int>(e % K);
+    if (j / XT < i / XT) continue;  // lower tiles are mirrored from the upper ones
+    float s = 0.0f;
+    for (int p = 0; p < splits; ++p) s += part[static_cast<long long>(p) * n + e];
+    const OutT v = static_cast<OutT>(alpha * static_cast<double>(s));
+    out[e] = v;
+    if (j / XT != i / XT) out[static_cast<long long>(j) * K + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ damping (gptq.py:115-117)
+// diag = where(diag != 0, diag, 1); diag += damp * mean(diag).  One CTA; fp64 tree mean.
+__global__ void __launch_bounds__(1024)
+    damp_diagonal(double* __restrict__ A, int K, double damp) {
+  __shared__ double s_part[32];
+  __shared__ double s_mean;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const double d = A[static_cast<long long>(i) * K + i];
+    acc += (d != 0.0) ? d : 1.0;  // NaN != 0 keeps NaN, like np.where(diag, diag, 1.0)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
+    s_mean = t / static_cast<double>(K);
+  }
+  __syncthreads();
+  const double add = damp * s_mean;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const long long p = static_cast<long long>(i) * K + i;
+    const double d = A[p];
+    A[p] = ((d != 0.0) ? d : 1.0) + add;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    copy_f64(const double* __restrict__ a, double* __restrict__ b, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    b[i] = a[i];
+}
+
+__global__ void __launch_bounds__(256)
+    copy_diag_f64(const double* __restrict__ a, double* __restrict__ b, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) b[static_cast<long long>(i) * K + i] = a[static_cast<long long>(i) * K + i];
+}
+
+// ------------------------------------------------------------------ Cholesky (fp64, lower, in place)
+constexpr int CB = 32;    // block size
+constexpr int CR = 128;   // panel rows per CTA
+
+// Panel step at column block j: every CTA factors the CB x CB diagonal block in shared memory
+// (redundantly: it is tiny) and solves its CR rows of the panel  X * L_jj^T = A[rows, j:j+CB];
+// CTA 0 also stores the factored diagonal block.  info != 0 flags a non-positive pivot.
+__global__ void __launch_bounds__(CR)
+    chol_panel(double* __restrict__ A, int K, int j, int* __restrict__ info) {
+  __shared__ double D[CB][CB + 1];
+  const int tid = threadIdx.x;
+  const int nb = min(CB, K - j);
+  for (int e = tid; e < CB * CB; e += CR) {
+    const int r = e / CB, c = e % CB;
+    D[r][c] = (r < nb && c <= r) ? A[static_cast<long long>(j + r) * K + j + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {  // unblocked right-looking factorisation of D
+    if (tid == 0) {
+      const double p = D[k][k];
+      if (!(p > 0.0)) atomicExch(info, j + k + 1);
+      D[k][k] = sqrt(p);
+    }
+    __syncthreads();
+    if (tid > k && tid < nb) D[tid][k] /= D[k][k];
+    __syncthreads();
+    // trailing update: thread t owns row t (t > k), columns k+1..t
+    if (tid > k && tid < nb) {
+      const double l = D[tid][k];
+      for (int c = k + 1; c <= tid; ++c) D[tid][c] -= l * D[c][k];
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < CB * CB; e += CR) {
+      const int r = e / CB, c = e % CB;
+      if (r < nb && c < nb) A[static_cast<long long>(j + r) * K + j + c] = (c <= r) ? D[r][c] : 0.0;
+    }
+  }
+  const int row = j + nb + blockIdx.x * CR + tid;
+  if (row < K) {
+    double x[CB];
+    double* a = A + static_cast<long long>(row) * K + j;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) x[c] = c < nb ? a[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      if (c < nb) {
+        double s = x[c];
+#pragma unroll
+        for (int m = 0; m < CB; ++m)
+          if (m < c) s -= x[m] * D[c][m];
+        x[c] = s / D[c][c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < nb) a[c] = x[c];
+  }
+}
+
+// Trailing update A[r, c] -= sum_k P[r, k] P[c, k] for the lower tiles of the trailing matrix,
+// P = A[j+CB:, j:j+CB].  64 x 64 tile per CTA, 4 x 4 per thread.
+__global__ void __launch_bounds__(256)
+    chol_syrk(double* __restrict__ A, int K, int j) {
+  __shared__ double Pr[64][CB + 1];
+  __shared__ double Pc[64][CB + 1];
+  const int base = j + CB;
+  const int nt = (K - base + 63) / 64;
+  // lower-triangular tile index: blockIdx.x -> (tr >= tc)
+  int tr = 0, left = blockIdx.x;
+  while (left > tr) {
+    left -= tr + 1;
+    ++tr;
+  }
+  const int tc = left;
+  (void)nt;
+  const int r0 = base + tr * 64, c0 = base + tc * 64;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * CB; e += 256) {
+    const int r = e / CB, k = e % CB;
+    Pr[r][k] = (r0 + r < K) ? A[static_cast<long long>(r0 + r) * K + j + k] : 0.0;
+    Pc[r][k] = (c0 + r < K) ? A[static_cast<long long>(c0 + r) * K + j + k] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4] = {};
+#pragma unroll 8
+  for (int k = 0; k < CB; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = Pr[ty + 16 * u][k];
+      b[u] = Pc[tx + 16 * u][k];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + ty + 16 * u;
+    if (r >= K) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = c0 + tx + 16 * v;
+      if (c <= r) A[static_cast<long long>(r) * K + c] -= acc[u][v];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ triangular inverse (fp32, lower)
+constexpr int TB = 64;
+
+// L32 = float(L64) on the lower triangle, 0 above (strtri's float32 cast of the factor).
+__global__ void __launch_bounds__(256)
+    lower_to_f32(const double* __restrict__ A, float* __restrict__ L, int K) {
+  const long long n = static_cast<long long>(K) * K;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(e / K), c = static_cast<int>(e % K);
+    L[e] = c <= r ? static_cast<float>(A[e]) : 0.0f;
+  }
+}
+
+// Inverse of each TB x TB diagonal block (forward substitution, one thread per column),
+// written into the diagonal blocks of Y; the rest of Y's upper triangle is zeroed by trtri_cols.
+__global__ void __launch_bounds__(TB)
+    trtri_diag(const float* __restrict__ L, float* __restrict__ Y, int K) {
+  __shared__ float D[TB][TB + 1];
+  __shared__ float R[TB][TB + 1];
+  const int b0 = blockIdx.x * TB;
+  const int nb = min(TB, K - b0);
+  const int c = threadIdx.x;
+  for (int e = c; e < TB * TB; e += TB) {
+    const int r = e / TB, k = e % TB;
+    D[r][k] = (r < nb && k < nb) ? L[static_cast<long long>(b0 + r) * K + b0 + k] : (r == k ? 1.0f : 0.0f);
+  }
+  __syncthreads();
+  // column c of the inverse: y[r] = (delta_rc - sum_{m<r} D[r][m] y[m]) / D[r][r]
+  for (int r = 0; r < TB; ++r) {
+    float s = (r == c) ? 1.0f : 0.0f;
+    for (int m = c; m < r; ++m) s = fmaf(-D[r][m], R[m][c], s);
+    R[r][c] = (r < c) ? 0.0f : __fdiv_rn(s, D[r][r]);
+  }
+  __syncthreads();
+  for (int e = c; e < TB * TB; e += TB) {
+    const int r = e / TB, k = e % TB;
+    if (r < nb && k < nb) Y[static_cast<long long>(b0 + r) * K + b0 + k] = R[r][k];
+  }
+}
+
+// Block column j, column slice s (TS columns): for i = j+1 .. : Y[i, js] = -Dinv[i] * sum_{k=j}^{i-1} L[i,k] Y[k, js].
+// One CTA owns its slice top to bottom, so the recurrence needs no grid-wide sync.
+constexpr int TS = 16;
+__global__ void __launch_bounds__(256)
+    trtri_cols(const float* __restrict__ L, float* __restrict__ Y, int K) {
+  __shared__ float Ls[TB][TB + 1];
+  __shared__ float Ys[TB][TS + 1];
+  __shared__ float Ss[TB][TS + 1];
+  const int nblk = (K + TB - 1) / TB;
+  const int j = blockIdx.x / (TB / TS), s = blockIdx.x % (TB / TS);
+  const int cj = j * TB + s * TS;  // first global column of the slice
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, cq = (tid & 3) * 4;  // thread: row r (0..63), 4 columns cq..cq+3
+  // zero the strictly-upper blocks of this slice (rows above block j)
+  for (long long e = tid; e < static_cast<long long>(j) * TB * TS; e += 256) {
+    const int rr = static_cast<int>(e / TS), cc = static_cast<int>(e % TS);
+    if (cj + cc < K) Y[static_cast<long long>(rr) * K + cj + cc] = 0.0f;
+  }
+  for (int i = j + 1; i < nblk; ++i) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = j; k < i; ++k) {
+      __syncthreads();
+      for (int e = tid; e < TB * TB; e += 256) {
+        const int rr = e / TB, kk = e % TB;
+        const int gr = i * TB + rr, gc = k * TB + kk;
+        Ls[rr][kk] = (gr < K && gc < K) ? L[static_cast<long long>(gr) * K + gc] : 0.0f;
+      }
+      for (int e = tid; e < TB * TS; e += 256) {
+        const int rr = e / TS, cc = e % TS;
+        const int gr = k * TB + rr, gc = cj + cc;
+        Ys[rr][cc] = (gr < K && gc < K) ? Y[static_cast<long long>(gr) * K + gc] : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll 16
+      for (int kk = 0; kk < TB; ++kk) {
+        const float l = Ls[r][kk];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(l, Ys[kk][cq + u], acc[u]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Ss[r][cq + u] = acc[u];
+    // Dinv[i] (already in Y's diagonal block) into Ls
+    for (int e = tid; e < TB * TB; e += 256) {
+      const int rr = e / TB, kk = e % TB;
+      const int gr = i * TB + rr, gc = i * TB + kk;
+      Ls[rr][kk] = (gr < K && gc < K && kk <= rr) ? Y[static_cast<long long>(gr) * K + gc] : 0.0f;
+    }
+    __syncthreads();
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 16
+    for (int kk = 0; kk < TB; ++kk) {
+      const float d = Ls[r][kk];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[u] = fmaf(d, Ss[kk][cq + u], o[u]);
+    }
+    const int gr = i * TB + r;
+    if (gr < K) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cj + cq + u < K) Y[static_cast<long long>(gr) * K + cj + cq + u] = -o[u];
+    }
+    __syncthreads();  // Y[i, slice] is read back (as Ys) in later iterations of i
+  }
+}
+
+// out = (a * wa + b * wb) / (wa + wb) elementwise in fp64 (qsv_utils.py:84-88).
+__global__ void __launch_bounds__(256)
+    weighted_mean_f64(const double* __restrict__ a, double wa, const double* __restrict__ b, double wb,
+                      double* __restrict__ out, long long n) {
+  const double tot = wa + wb;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __ddiv_rn(__dadd_rn(__dmul_rn(a[i], wa), __dmul_rn(b[i], wb)), tot);  // no FMA contraction
+}
+
+int xtx_splits(long long T, int K, int sm_count) {
+  const int nb = (K + XT - 1) / XT;
+  const long long tiles = static_cast<long long>(nb) * (nb + 1) / 2;
+  long long want = (2LL * sm_count + tiles - 1) / tiles;
+  const long long max_by_t = (T + 4 * XK - 1) / (4 * XK);
+  if (want > max_by_t) want = max_by_t;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+template <typename OutT>
+cudaError_t xtx_impl(const float* x, long long T, long long K, double alpha, OutT* out, void* ws,
+                     int sm_count, cudaStream_t st) {
+  if (K <= 0) return cudaSuccess;
+  const int k = static_cast<int>(K);
+  const int nb = (k + XT - 1) / XT;
+  const unsigned tiles = static_cast<unsigned>(static_cast<long long>(nb) * (nb + 1) / 2);
+  const int splits = ws ? xtx_splits(T, k, sm_count) : 1;
+  if (splits <= 1) {
+    xtx_tile<OutT><<<dim3(tiles, 1), 256, 0, st>>>(x, T, k, alpha, out, nullptr, T > 0 ? T : 1);
+    return count_launch();
+  }
+  long long per = (T + splits - 1) / splits;
+  per = (per + XK - 1) / XK * XK;
+  xtx_tile<OutT><<<dim3(tiles, splits), 256, 0, st>>>(x, T, k, alpha, out, static_cast<float*>(ws), per);
+  xtx_reduce<OutT><<<sm_count * 4, 256, 0, st>>>(static_cast<const float*>(ws), splits, k, alpha, out);
+  return count_launch(2);
+}
+
+}  // namespace
+
+size_t xtx_workspace_bytes(long long T, long long K, int sm_count) {
+  if (K <= 0) return 0;
+  const int s = xtx_splits(T, static_cast<int>(K), sm_count);
+  return s <= 1 ? 0 : static_cast<size_t>(s) * K * K * sizeof(float);
+}
+
+cudaError_t launch_xtx_f64(const float* x, long long T, long long K, double alpha, double* out,
+                           void* ws, int sm_count, cudaStream_t st) {
+  return xtx_impl<double>(x, T, K, alpha, out, ws, sm_count, st);
+}
+
+cudaError_t launch_xtx_f32(const float* x, long long T, long long K, double alpha, float* out,
+                           void* ws, int sm_count, cudaStream_t st) {
+  return xtx_impl<float>(x, T, K, alpha, out, ws, sm_count, st);
+}
+
+// ws: A (K*K doubles) | L32 (K*K floats) | Y (K*K floats) | info (int, 256 B slot)
+size_t hessian_inverse_workspace_bytes(long long K) {
+  return static_cast<size_t>(K) * K * (sizeof(double) + 2 * sizeof(float)) + 256;
+}
+
+cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, int mutate_diagonal,
+                                   float* hinv, void* ws, int* info_out, int sm_count,
+                                   cudaStream_t st) {
+  if (K <= 0) return cudaSuccess;
+  const int k = static_cast<int>(K);
+  const long long n = K * K;
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  double* A = reinterpret_cast<double*>(p);
+  float* L32 = reinterpret_cast<float*>(p + n * sizeof(double));
+  float* Y = L32 + n;
+  int* info = reinterpret_cast<int*>(p + n * (sizeof(double) + 2 * sizeof(float)));
+  int launches = 0;
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const unsigned cgrid = static_cast<unsigned>(sm_count * 8);
+  copy_f64<<<cgrid, 256, 0, st>>>(hessian, A, n); ++launches;
+  damp_diagonal<<<1, 1024, 0, st>>>(A, k, damp); ++launches;
+  if (mutate_diagonal) {  // the reference leaves the damped diagonal in the caller's Hessian
+    copy_diag_f64<<<(k + 255) / 256, 256, 0, st>>>(A, hessian, k); ++launches;
+  }
+  for (int j = 0; j < k; j += CB) {
+    const int below = k - j - CB;
+    const unsigned pgrid = below > 0 ? static_cast<unsigned>((below + CR - 1) / CR) : 1u;
+    chol_panel<<<pgrid, CR, 0, st>>>(A, k, j, info); ++launches;
+    if (below > 0) {
+      const int nt = (below + 63) / 64;
+      chol_syrk<<<static_cast<unsigned>(nt * (nt + 1) / 2), 256, 0, st>>>(A, k, j); ++launches;
+    }
+  }
+  lower_to_f32<<<cgrid, 256, 0, st>>>(A, L32, k); ++launches;
+  const int nblk = (k + TB - 1) / TB;
+  trtri_diag<<<nblk, TB, 0, st>>>(L32, Y, k); ++launches;
+  trtri_cols<<<nblk * (TB / TS), 256, 0, st>>>(L32, Y, k); ++launches;
+  e = count_launch(launches);
+  if (e != cudaSuccess) return e;
+  // H^-1 = Y^T Y (einsum "ji,jk->ik"): the same contraction as the Hessian itself.  The split
+  // workspace may reuse A + L32, which are dead by now.
+  const size_t need = xtx_workspace_bytes(K, K, sm_count);
+  void* xws = need > 0 && need <= static_cast<size_t>(n) * (sizeof(double) + sizeof(float)) ? ws : nullptr;
+  e = xtx_impl<float>(Y, K, K, 1.0, hinv, xws, sm_count, st);
+  if (e != cudaSuccess) return e;
+  if (info_out) {
+    e = cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st);
+  }
+  return e;
+}
+
+cudaError_t launch_weighted_mean_f64(const double* a, double wa, const double* b, double wb,
+                                     double* out, long long n, int sm_count, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  weighted_mean_f64<<<sm_count * 8, 256, 0, st>>>(a, wa, b, wb, out, n);
+  return count_launch();
+}
+
+}  // namespace aeqb

@@ -184,6 +184,43 @@ AEQB_API int aeqb_mse_scale_rows_f32(const float* x, int64_t rows, int64_t cols,
 AEQB_API int aeqb_hadamard_rows_f32(const float* x, int64_t rows, int64_t cols, int64_t n,
                                     float* out, void* stream);
 
+/* ---------------------------------------------------------------- GPTQ
+ * hessian[k, k] (float64) = alpha * X^T X with X = x viewed as [tokens, k], fp32
+ * accumulation promoted by the float64 scalar: gptq.calibrate
+ * (algorithms/uniform_quantize/gptq.py:100-106; alpha = 2 / num_samples).
+ *   ws: aeqb_xtx_workspace_bytes(tokens, k) bytes (may be 0 -> NULL allowed). */
+AEQB_API size_t aeqb_xtx_workspace_bytes(int64_t tokens, int64_t k);
+AEQB_API int aeqb_xtx_f32(const float* x, int64_t tokens, int64_t k, double alpha, double* hessian,
+                          void* ws, void* stream);
+
+/* hinv[k, k] (float32) = inverse of the damped Hessian, gptq._prepare_hessian_inverse
+ * (gptq.py:111-128): zero diagonal entries -> 1, + damp * mean(diag), float64
+ * Cholesky, float32 triangular inverse, L^-T L^-1.
+ *   keep_damped_diagonal != 0 reproduces the reference's side effect of leaving the
+ *   damped diagonal in the caller's `hessian` (np.diag returns a view, gptq.py:114,123).
+ *   info: DEVICE int, 0 on success, i > 0 if the leading minor of order i is not
+ *   positive definite (np.linalg.cholesky would raise LinAlgError).
+ *   ws: aeqb_hessian_inverse_workspace_bytes(k) bytes. */
+AEQB_API size_t aeqb_hessian_inverse_workspace_bytes(int64_t k);
+AEQB_API int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp,
+                                      int keep_damped_diagonal, float* hinv, void* ws, int* info,
+                                      void* stream);
+
+/* The 64-column lazy-block OBS loop, gptq._apply_gptq (gptq.py:131-216).
+ *   w_work: [rows, k] fp32 COPY of the weight, updated in place (gptq.py:139 copies too).
+ *   scale / zp: scale_cols entries per row: 1 (per channel), k / block (blockwise,
+ *   gptq.py:177-189) or 0 (one entry for the whole tensor).  zp may be NULL (zeros).
+ *   blocksize: 64 (the reference's only value).  q: [rows, k] int8. */
+AEQB_API int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
+                                    const float* scale, const int32_t* zp, int64_t scale_cols,
+                                    int block, int bits, int symmetric, int blocksize, int8_t* q,
+                                    void* stream);
+
+/* out = (a * wa + b * wb) / (wa + wb), float64: the sample-weighted Hessian mean of
+ * qsv_utils._gptq_merge_hessian (utils/qsv_utils.py:71-88).  out may alias a or b. */
+AEQB_API int aeqb_hessian_merge_f64(const double* a, double wa, const double* b, double wb,
+                                    double* out, int64_t n, void* stream);
+
 /* ---------------------------------------------------------------- unfused pieces
  * tensor_zp_scale_from_min_max (uqt:492-586) on n (min, max[, clip]) triples.
  * blockwise != 0 applies the bf16->fp16 scale rounding (uqt:577-581) and, with

@@ -128,9 +128,10 @@ def test_qsv_update_rules():
   assert u["min"][0] == -1.0 and u["max"][0] == 2.0
   a = {"min": np.array([0.0]), "max": np.array([1.0]), "hessian": np.eye(2) * 2.0, "num_samples": 2}
   b = {"min": np.array([0.0]), "max": np.array([1.0]), "hessian": np.eye(2) * 8.0, "num_samples": 6}
-  m = qsv_utils.gptq_and_moving_average_update(a, b)
-  np.testing.assert_allclose(m["hessian"], np.eye(2) * 6.5)
-  assert m["num_samples"] == 8
+  # the K x K Hessian merge is device work (aeqb_hessian_merge_f64): no GPU here -> it must raise
+  with pytest.raises(RuntimeError, match="no CPU fallback"):
+    qsv_utils.gptq_and_moving_average_update(a, b)
+  assert qsv_utils.gptq_and_moving_average_update({}, b) is b
 
 
 def test_layout_helpers():
