@@ -1,0 +1,124 @@
+"""Multi-GPU sharding of the requantisation path: one process per GPU, tensors as units.
+
+Every weight tensor is an independent unit of work (the reference walks them one op
+at a time with no cross-tensor state, params_generator.py:110-183), so the path
+shards with NO data-path collective: `assign_tensors` bin-packs tensors onto ranks by
+bytes (longest-processing-time first), each rank requantises the tensors it owns, and
+quantised payloads stay with their owner.  The one real exchange is small: every rank
+needs every tensor's scale vector (4 B per row per-channel, 2-4 B per block) to write
+the model's quantisation parameters, so `allgather_vectors` does ONE all-gather of a
+flat, offset-indexed buffer (NCCL for CUDA tensors, gloo for CPU tensors).
+
+Works unchanged at world size 1 (no process group needed).
+"""
+from __future__ import annotations
+
+import heapq
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def assign_tensors(sizes: Sequence[int], world: int) -> list[int]:
+  """Rank that owns each tensor: LPT bin packing by size, ties broken by index (deterministic,
+  so every rank computes the same table without communicating)."""
+  if world < 1:
+    raise ValueError("world size must be >= 1")
+  order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+  heap = [(0, r) for r in range(world)]
+  heapq.heapify(heap)
+  owner = [0] * len(sizes)
+  for i in order:
+    load, r = heapq.heappop(heap)
+    owner[i] = r
+    heapq.heappush(heap, (load + int(sizes[i]), r))
+  return owner
+
+
+def owned(owner: Sequence[int], rank: int) -> list[int]:
+  return [i for i, r in enumerate(owner) if r == rank]
+
+
+def imbalance(sizes: Sequence[int], owner: Sequence[int], world: int) -> float:
+  """max rank load / mean rank load (1.0 = perfect)."""
+  loads = [0] * world
+  for s, r in zip(sizes, owner):
+    loads[r] += int(s)
+  mean = sum(loads) / world
+  return max(loads) / mean if mean else 1.0
+
+
+def _world(group) -> tuple[int, int]:
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(group), dist.get_world_size(group)
+  return 0, 1
+
+
+def allgather_vectors(local: dict[int, torch.Tensor], lengths: Sequence[int], owner: Sequence[int],
+                      group=None) -> list[torch.Tensor]:
+  """All ranks end up with every tensor's vector.
+
+  local:   {tensor index: 1-D tensor} for the tensors this rank owns (all one dtype / device).
+  lengths: vector length of EVERY tensor (known everywhere: it follows from the shapes).
+  One all_gather_into_tensor of a [world, max_rank_len] buffer; rank r's slots are its
+  tensors in index order, so offsets need no exchange.
+  """
+  rank, world = _world(group)
+  mine = owned(owner, rank)
+  if sorted(local) != mine:
+    raise ValueError(f"rank {rank} must supply exactly the tensors it owns: {mine}")
+  per_rank = [sum(int(lengths[i]) for i in owned(owner, r)) for r in range(world)]
+  width = max(per_rank) if per_rank else 0
+  if not local and width == 0:
+    return [torch.empty(0) for _ in lengths]
+  proto = next(iter(local.values())) if local else None
+  if world > 1 and proto is None:
+    raise ValueError("a rank without tensors cannot infer dtype / device; give every rank work")
+  flat = torch.zeros(width, dtype=proto.dtype, device=proto.device)
+  off = 0
+  for i in mine:
+    v = local[i].reshape(-1)
+    if v.numel() != int(lengths[i]):
+      raise ValueError(f"tensor {i}: expected {lengths[i]} values, got {v.numel()}")
+    flat[off:off + v.numel()] = v
+    off += v.numel()
+  if world == 1:
+    gathered = flat.reshape(1, width)
+  else:
+    buf = torch.empty(world * width, dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(buf, flat, group=group)
+    gathered = buf.reshape(world, width)
+  out: list[Optional[torch.Tensor]] = [None] * len(lengths)
+  for r in range(world):
+    off = 0
+    for i in owned(owner, r):
+      n = int(lengths[i])
+      out[i] = gathered[r, off:off + n]
+      off += n
+  return out  # type: ignore[return-value]
+
+
+def requantize_sharded(weights: Sequence[np.ndarray], compute: Callable[[list[np.ndarray]], list],
+                       scale_length: Callable[[np.ndarray], int], group=None,
+                       device: Optional[torch.device] = None):
+  """Shards `weights` over the process group, runs `compute` on the owned ones, all-gathers scales.
+
+  weights:      the model's weight arrays (every rank sees the same list; only owned ones are read).
+  compute:      owned arrays -> list of (q, packed, scale, extra) tuples, e.g.
+                `functools.partial(aeq_b200.host.requant_rows, bits=8)`.
+  scale_length: array -> number of scale entries (rows, or rows * cols / block).
+  Returns (owner table, {index: result tuple} for owned tensors, [scale vector of every tensor]).
+  """
+  rank, world = _world(group)
+  sizes = [int(w.size) * w.dtype.itemsize for w in weights]
+  owner = assign_tensors(sizes, world)
+  mine = owned(owner, rank)
+  results = compute([weights[i] for i in mine]) if mine else []
+  local = {}
+  for i, res in zip(mine, results):
+    s = torch.from_numpy(np.ascontiguousarray(res[2]).reshape(-1))
+    local[i] = s.to(device) if device is not None else s
+  scales = allgather_vectors(local, [scale_length(w) for w in weights], owner, group)
+  return owner, dict(zip(mine, results)), scales

@@ -51,8 +51,10 @@ def parse():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--tensors", type=int, default=64, help="[4096,4096] tensors per GPU")
   ap.add_argument("--e2e-tensors", type=int, default=16, help="stack size of the host-buffer arm")
-  ap.add_argument("--cpu-sample", type=int, default=12, help="tensors timed by the CPU baseline")
+  ap.add_argument("--cpu-sample", type=int, default=32, help="tensors timed by the CPU baseline")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--modes", default="headline", choices=["headline", "all"],
+                  help="all: also time OCTAV, MSE, Hadamard, calibration min/max and GPTQ (extra keys under modes)")
   return ap.parse_args()
 
 
@@ -62,15 +64,27 @@ def workload_name(t):
 
 
 # ------------------------------------------------------------------ CPU arms
-def cpu_pass(weights, mode):
+def cpu_one(w, mode):
   from oracle import aeq_oracle as O
-  for w in weights:
-    if mode == "int8":
-      O.minmax_requant(w, 8, True)
-    else:
-      r = O.minmax_requant(w, 4, True, block=32)
-      O.pack_bits(4, r["q"])
-      O.blockwise_scale_fp16(r["scale"])
+  if mode == "int8":
+    O.minmax_requant(w, 8, True)
+  else:
+    r = O.minmax_requant(w, 4, True, block=32)
+    O.pack_bits(4, r["q"])
+    O.blockwise_scale_fp16(r["scale"])
+
+
+def cpu_pass(weights, mode, threads=1):
+  """One pass of the reference's CPU path over `weights`.  The reference itself is a
+  single-threaded NumPy loop over tensors (params_generator.py:110-183); threads > 1 gives it
+  every host core by running independent tensors concurrently (NumPy releases the GIL)."""
+  if threads <= 1:
+    for w in weights:
+      cpu_one(w, mode)
+    return
+  from concurrent.futures import ThreadPoolExecutor
+  with ThreadPoolExecutor(max_workers=threads) as ex:
+    list(ex.map(lambda w: cpu_one(w, mode), weights))
 
 
 def cpu_weights(n):
@@ -87,16 +101,28 @@ def cpu_threads():
     return 1
 
 
+def host_threads():
+  try:
+    return max(1, len(os.sched_getaffinity(0)))
+  except Exception:
+    return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(n_sample):
-  """Oracle port of the reference path, bounded sample, single NumPy thread (as shipped)."""
+  """Oracle port of the reference path on a bounded sample: all host cores (tensors in
+  parallel) and, for the record, one core (how the reference ships)."""
+  threads = host_threads()
   ws = cpu_weights(n_sample)
-  out = {}
+  out = {"threads": threads}
   for mode in ("int8", "int4"):
-    cpu_pass(ws[:1], mode)  # warm-up
+    cpu_pass(ws[:threads], mode, threads)  # warm-up
     t0 = time.perf_counter()
-    cpu_pass(ws, mode)
+    cpu_pass(ws, mode, threads)
     dt = time.perf_counter() - t0
     out[mode] = n_sample * ROWS * COLS * 4 / dt / 1e9
+  t0 = time.perf_counter()
+  cpu_pass(ws[:2], "int8", 1)
+  out["int8_single_thread"] = 2 * ROWS * COLS * 4 / (time.perf_counter() - t0) / 1e9
   return out
 
 
@@ -105,32 +131,41 @@ def run_reference(a):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  n = max(1, min(a.cpu_sample, 4))
+  threads = host_threads()
+  n = max(threads, min(a.cpu_sample, 32))
   ws = cpu_weights(n)
-  for _ in range(max(1, min(a.warmup, 1))):
-    cpu_pass(ws[:1], "int8")
+  warm = max(1, min(a.warmup, 2))
+  for _ in range(warm):
+    cpu_pass(ws, "int8", threads)
   steps = max(1, min(a.steps, 5))
   t0 = time.perf_counter()
   for _ in range(steps):
-    cpu_pass(ws, "int8")
+    cpu_pass(ws, "int8", threads)
   dt = (time.perf_counter() - t0) / steps
   v = n * ROWS * COLS * 4 / dt / 1e9
   t1 = time.perf_counter()
-  cpu_pass(ws, "int4")
+  cpu_pass(ws, "int4", threads)
   v4 = n * ROWS * COLS * 4 / (time.perf_counter() - t1) / 1e9
-  sample = f"{n} of the workload's [{ROWS},{COLS}] tensors per step, {steps} steps"
+  t1 = time.perf_counter()
+  cpu_pass(ws[:2], "int8", 1)
+  v1 = 2 * ROWS * COLS * 4 / (time.perf_counter() - t1) / 1e9
+  sample = (f"{n} of the workload's [{ROWS},{COLS}] tensors per step, {steps} steps,"
+            f" {threads} threads over independent tensors")
   print(json.dumps({
       "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-      "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+      "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": {"workload": workload_name(a.tensors), "sample": sample},
-      "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                       "blas_threads_available": cpu_threads(), "host_cores": os.cpu_count()},
-      "modes": {"int8_perchannel": {"value": v}, "int4_block32_packed": {"value": v4}},
+      "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                       "single_thread_value": v1, "host_cores": os.cpu_count()},
+      "modes": {"int8_perchannel": {"value": v}, "int4_block32_packed": {"value": v4},
+                "int8_perchannel_single_thread": {"value": v1}},
       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
       "note": "reference arm = NumPy port of the reference CPU path (oracle/aeq_oracle.py, pinned"
-              " bit-exact to the reference); the reference is single-threaded NumPy on this path",
+              " bit-exact to the reference; the Python reference cannot travel to the GPU box)."
+              " The reference is single-threaded NumPy on this path; this arm additionally runs"
+              " independent tensors on every host core",
   }), flush=True)
 
 
@@ -179,6 +214,102 @@ class ClockSampler:
             "samples": len(sm)}
 
 
+# ------------------------------------------------------------------ the other rows of the path
+def extra_modes(dev, ws, peak, steps):
+  """Device-resident timings of the remaining hot-path rows on the same stack."""
+  import torch
+  from aeq_b200 import device
+  out = {}
+  T = min(len(ws), 16)
+  n_bytes = T * ROWS * COLS * 4
+
+  def timeit(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+  reps = max(3, min(steps, 10))
+
+  def octav(bits, block):
+    def run():
+      for w in ws[:T]:
+        if block:
+          c = device.octav_clip_blocks(w, block, bits)
+          device.requant_blocks(w, block, bits, clip=c, want_q=False, want_packed=True)
+        else:
+          c = device.octav_clip_rows(w, bits)
+          device.requant_rows(w, bits, True, clip=c)
+    return run
+
+  for name, fn, bpw in (("octav_int4_perchannel", octav(4, 0), 9.0),
+                        ("octav_int4_block32_packed", octav(4, 32), 8.5625 + 10 * 4 / 32)):
+    ms = timeit(fn, reps)
+    out[name] = {"value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": T, "bytes_per_weight": bpw,
+                 "roofline_frac": (n_bytes / 4) * bpw / ms / 1e6 / peak}
+
+  def mse():
+    for w in ws[:T]:
+      s = device.mse_scale_rows(w, 0.05408)
+      device.quantize(w, s.reshape(-1), None, 8, True, ROWS, COLS)
+  ms = timeit(mse, reps)
+  out["mse_int8_perchannel"] = {"value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": T,
+                                "bytes_per_weight": 9.0, "roofline_frac": (n_bytes / 4) * 9.0 / ms / 1e6 / peak}
+
+  rot = torch.empty_like(ws[0])
+
+  def hadamard():
+    for w in ws[:T]:
+      device.hadamard_rows(w, COLS, out=rot)
+      c = device.octav_clip_rows(rot, 4)
+      device.requant_rows(rot, 4, True, clip=c)
+  ms = timeit(hadamard, reps)
+  out["hadamard4096_octav_int4"] = {"value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": T,
+                                    "bytes_per_weight": 17.0,
+                                    "roofline_frac": (n_bytes / 4) * 17.0 / ms / 1e6 / peak}
+
+  def had_only():
+    for w in ws[:T]:
+      device.hadamard_rows(w, COLS, out=rot)
+  ms = timeit(had_only, reps)
+  out["hadamard4096_rotate_only"] = {"value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": T,
+                                     "bytes_per_weight": 8.0,
+                                     "roofline_frac": (n_bytes / 4) * 8.0 / ms / 1e6 / peak}
+
+  # calibration: per-batch min/max with the (-3e38, 3e38) filter over [8, 512, 4096] activations
+  acts = [w.view(8, 512, 4096) for w in ws[:T]]
+
+  def calib():
+    for a in acts:
+      device.minmax_tensor(a, -3e38, 3e38)
+  ms = timeit(calib, reps)
+  out["calibration_minmax"] = {"value": n_bytes / ms / 1e6, "unit": "activation GB/s", "ms_per_step": ms,
+                               "batches": T, "bytes_per_element": 4.0,
+                               "roofline_frac": n_bytes / ms / 1e6 / peak}
+
+  # GPTQ on one [4096, 4096] layer: Hessian from 8192 tokens, damped inverse, OBS loop
+  x = torch.randn(8, 1024, COLS, device=dev)
+  ms_h = timeit(lambda: device.xtx(x, 2.0 / 8), 3)
+  h = device.xtx(x, 2.0 / 8)
+  ms_inv = timeit(lambda: device.hessian_inverse(h, 0.01), 2)
+  hinv = device.hessian_inverse(h, 0.01)
+  w = ws[0]
+  sc = w.abs().amax(dim=1) / 7.0
+  ms_q = timeit(lambda: device.gptq_quantize(w, hinv, sc, None, 0, 4, True), 2)
+  out["gptq_int4_4096x4096"] = {
+      "value": ROWS * COLS * 4 / (ms_inv + ms_q) / 1e6, "ms_hessian_8192_tokens": ms_h,
+      "hessian_tflops": 2.0 * 8192 * COLS * COLS / ms_h / 1e9,
+      "ms_hessian_inverse": ms_inv, "ms_obs_loop": ms_q,
+      "obs_loop_tflops": 1.0 * ROWS * COLS * COLS / ms_q / 1e9,
+      "note": "value = fp32 weight bytes / (inverse + OBS loop) for one layer, Hessian given"}
+  return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def main():
   a = parse()
@@ -216,13 +347,19 @@ def main():
   n_bytes = T * ROWS * COLS * 4
 
   state = {}
+  # Per-channel scales of this rank's tensors live in ONE flat buffer (each tensor's scale output
+  # is a view into it), so the path's single collective needs no packing step.
+  flat_scales = torch.empty(T * ROWS, dtype=torch.float32, device=dev)
   gathered = (torch.empty(world * T * ROWS, dtype=torch.float32, device=dev) if world > 1 else None)
+  state["r8"] = [device.Requantized(
+      torch.empty((ROWS, COLS), dtype=torch.int8, device=dev), None,
+      flat_scales[i * ROWS:(i + 1) * ROWS].view(ROWS, 1),
+      torch.empty((ROWS, 1), dtype=torch.int32, device=dev)) for i in range(T)]
 
   def step_int8():
-    state["r8"] = device.requant_rows_batch(ws, 8, True, outs=state.get("r8"))
+    device.requant_rows_batch(ws, 8, True, outs=state["r8"])
     if world > 1:  # the path's one collective: all ranks learn every per-channel scale
-      flat = torch.cat([o.scale.view(-1) for o in state["r8"]])
-      dist.all_gather_into_tensor(gathered, flat)
+      dist.all_gather_into_tensor(gathered, flat_scales)
 
   def step_int4():
     state["b4"] = device.requant_blocks_batch(ws, 32, 4, outs=state.get("b4"))
@@ -268,7 +405,7 @@ def main():
   l0 = lib.aeqb_launch_count()
   e0.record()
   for _ in range(a.steps):
-    state["r8"] = device.requant_rows_batch(ws, 8, True, outs=state["r8"])
+    device.requant_rows_batch(ws, 8, True, outs=state["r8"])
   e1.record()
   torch.cuda.synchronize()
   k_launches = lib.aeqb_launch_count() - l0
@@ -283,6 +420,15 @@ def main():
   torch.cuda.synchronize()
   k4_ms = e0.elapsed_time(e1) / a.steps
   achieved4 = (n_bytes / 4) * 4.5625 / k4_ms / 1e6
+
+  # dram bytes per launch from the committed `ncu --set full` capture of this kernel, scaled by
+  # tensor count when the capture used a different stack size (profiles/traffic.json)
+  traffic = None
+  try:
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["requant_rows_stream"]
+    traffic = tj["dram_bytes_per_launch"] * (alg_per_launch / tj["algorithmic_bytes_per_launch"])
+  except Exception:
+    pass
 
   # ---- e2e: host-buffer C-ABI call, pinned host arrays in and out
   Te = max(1, min(a.e2e_tensors, T))
@@ -313,14 +459,19 @@ def main():
   # spot-check the e2e result against the device-resident path (same arithmetic)
   ok = bool((torch.from_numpy(e_outs[0][0]).to(dev) == state["r8"][0].q).all())
 
+  extra = {}
+  if a.modes == "all" and rank == 0 and world == 1:
+    extra = extra_modes(dev, ws, peak, a.steps)
+
   cpu = None
   if rank == 0 and not a.no_cpu_baseline:
     c = cpu_baseline(a.cpu_sample)
-    cpu = {"value": c["int8"], "unit": UNIT, "cores": 1, "kind": "port",
+    cpu = {"value": c["int8"], "unit": UNIT, "cores": c["threads"], "kind": "port",
            "sample": f"{a.cpu_sample} of the workload's [{ROWS},{COLS}] tensors, one pass, oracle/aeq_oracle.py"
-                     " (NumPy restatement pinned bit-exact to the reference; single-threaded like the reference)",
-           "int4_block32_packed": c["int4"], "host_cores": os.cpu_count(),
-           "blas_threads_available": cpu_threads()}
+                     f" (NumPy restatement pinned bit-exact to the reference), {c['threads']} threads over"
+                     " independent tensors",
+           "int4_block32_packed": c["int4"], "single_thread_value": c["int8_single_thread"],
+           "host_cores": os.cpu_count()}
 
   if rank == 0:
     print(json.dumps({
@@ -335,9 +486,9 @@ def main():
             "int8_perchannel": {"value": value8, "ms_per_step": ms8, "launches_per_step": launches8 / a.steps},
             "int4_block32_packed": {"value": value4, "ms_per_step": ms4, "launches_per_step": launches4 / a.steps,
                                     "roofline_frac": achieved4 / peak, "achieved_hbm_gbs": achieved4,
-                                    "bytes_per_weight": 4.5625}},
+                                    "bytes_per_weight": 4.5625}, **extra},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": traffic,
                      "kernel": "requant_rows_stream<32768,8>", "bytes_per_weight": 5.0,
                      "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": k_ms,
                      "peak_source": peak_src},

@@ -1,0 +1,94 @@
+"""Host-side logic of the multi-GPU path on CPU: LPT assignment and the one all-gather of scale
+vectors, run at world size 2 over gloo (the N > 1 plumbing; the arithmetic itself is GPU-only,
+so the per-rank `compute` here is the oracle standing in as the checker's reference)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aeq_b200 import sharding
+from oracle import aeq_oracle as O
+
+
+def test_assignment_is_balanced_and_deterministic():
+  sizes = [4096 * 4096 * 4] * 7 + [16384 * 2048 * 4] * 4 + [256 * 2048 * 4] * 9
+  for world in (1, 2, 4, 8):
+    owner = sharding.assign_tensors(sizes, world)
+    assert owner == sharding.assign_tensors(sizes, world)
+    assert set(owner) <= set(range(world))
+    assert sorted(sum((sharding.owned(owner, r) for r in range(world)), [])) == list(range(len(sizes)))
+    assert sharding.imbalance(sizes, owner, world) < 1.15
+  # Gemma-2B-shaped layer set x 18 layers over 8 GPUs (BASELINE configs[2])
+  layer = [2048 * 2048] * 2 + [256 * 2048] * 2 + [16384 * 2048] * 2 + [2048 * 16384]
+  sizes = [4 * s for s in layer] * 18
+  assert sharding.imbalance(sizes, sharding.assign_tensors(sizes, 8), 8) < 1.02
+  with pytest.raises(ValueError):
+    sharding.assign_tensors([1], 0)
+
+
+def test_single_process_path_needs_no_group():
+  ws = [O.synthetic_weight(8, 64, i) for i in range(3)]
+  compute = lambda arrs: [(r["q"], None, r["scale"], r["zero_point"])
+                          for r in (O.minmax_requant(a, 8, True) for a in arrs)]
+  owner, mine, scales = sharding.requantize_sharded(ws, compute, lambda w: w.shape[0])
+  assert owner == [0, 0, 0] and sorted(mine) == [0, 1, 2]
+  for w, s in zip(ws, scales):
+    np.testing.assert_array_equal(s.numpy(), O.minmax_requant(w, 8, True)["scale"].reshape(-1))
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shapes, block, out_dir):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    ws = [O.synthetic_weight(r, c, i) for i, (r, c) in enumerate(shapes)]
+    calls = []
+
+    def compute(arrs):
+      calls.append(len(arrs))
+      out = []
+      for a in arrs:
+        r = O.minmax_requant(a, 4 if block else 8, True, block=block)
+        out.append((r["q"], None, r["scale"], None))
+      return out
+
+    length = (lambda w: w.size // block) if block else (lambda w: w.shape[0])
+    owner, mine, scales = sharding.requantize_sharded(ws, compute, length)
+    assert sorted(mine) == sharding.owned(owner, rank)
+    assert calls == [len(mine)]
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), owner=np.array(owner),
+             **{f"s{i}": s.numpy() for i, s in enumerate(scales)})
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("block", [0, 32])
+def test_world2_gloo_allgather_of_scales(tmp_path, block):
+  """Ragged tensor set over 2 ranks: both ranks end with every tensor's scale vector."""
+  shapes = [(64, 256), (8, 1024), (130, 64), (16, 512), (3, 2048)]
+  port = _free_port()
+  mp.start_processes(_worker, args=(2, port, shapes, block, str(tmp_path)), nprocs=2, join=True,
+                     start_method="spawn")
+  got = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+  assert list(got[0]["owner"]) == list(got[1]["owner"])
+  assert set(got[0]["owner"]) == {0, 1}
+  for i, (r, c) in enumerate(shapes):
+    want = O.minmax_requant(O.synthetic_weight(r, c, i), 4 if block else 8, True, block=block)["scale"]
+    for g in got:
+      np.testing.assert_array_equal(g[f"s{i}"], want.reshape(-1))
+
+
+def test_allgather_validates_ownership():
+  with pytest.raises(ValueError, match="must supply exactly the tensors it owns"):
+    sharding.allgather_vectors({1: torch.zeros(3)}, [3, 3], [0, 0])
+  with pytest.raises(ValueError, match="expected 3 values"):
+    sharding.allgather_vectors({0: torch.zeros(2)}, [3], [0])
