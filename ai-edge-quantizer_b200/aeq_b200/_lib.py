@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaeqb200.so")
+LIB_PATH = os.environ.get("AEQB200_LIB") or os.path.join(_HERE, "libaeqb200.so")  # env: A/B builds
 HEADER_PATH = os.path.normpath(
     os.path.join(_HERE, "..", "..", "include", "aeqb200.h"))
 
@@ -40,6 +40,7 @@ SIGNATURES = {
     "aeqb_requant_rows_batch_f32": (_I, [_P, _L, _I, _I, _P]),
     "aeqb_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I, _P]),
     "aeqb_minmax_workspace_bytes": (_c.c_size_t, []),
+    "aeqb_minmax_tensors_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P]),
     "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),
     "aeqb_row_stats_f32": (_I, [_P, _L, _L, _P, _P, _P, _P]),
     "aeqb_minmax_blocks_f32": (_I, [_P, _L, _L, _I, _P, _P, _P]),
@@ -71,6 +72,11 @@ class BlocksJob(_c.Structure):
   """aeqb_blocks_job (include/aeqb200.h)."""
   _fields_ = [("x", _P), ("rows", _L), ("cols", _L), ("clip", _P), ("q", _P),
               ("packed", _P), ("scale", _P), ("scale_f16", _P)]
+
+
+class MinmaxJob(_c.Structure):
+  """aeqb_minmax_job (include/aeqb200.h)."""
+  _fields_ = [("x", _P), ("n", _L), ("out2", _P)]
 
 
 class AeqbError(RuntimeError):

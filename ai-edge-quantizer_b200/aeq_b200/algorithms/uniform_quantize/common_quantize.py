@@ -82,6 +82,48 @@ def get_activation_min_max(tensor_content, valid_float_range_min: float | None =
   return {"min": np.reshape(mm[0], shape), "max": np.reshape(mm[1], shape)}
 
 
+def get_activation_min_max_batch(contents: Sequence, valid_float_range_min: float | None = None,
+                                 valid_float_range_max: float | None = None) -> list[dict]:
+  """`get_activation_min_max` for all float tensors of a calibration step in ONE device launch
+  (per 64 tensors) and one download; integer tensors take the single-tensor path."""
+  from ... import device
+  out: list = [None] * len(contents)
+  idx, dev_tensors = [], []
+  for i, c in enumerate(contents):
+    if isinstance(c, np.ndarray) and np.issubdtype(c.dtype, np.integer):
+      out[i] = get_activation_min_max(c, valid_float_range_min, valid_float_range_max)
+    else:
+      idx.append(i)
+      dev_tensors.append(hostio.to_device(c, np.float32).reshape(-1))
+  if idx:
+    mm = hostio.to_host(device.minmax_tensors(dev_tensors, valid_float_range_min,
+                                              valid_float_range_max))
+    for k, i in enumerate(idx):
+      shape = (1,) * contents[i].ndim
+      out[i] = {"min": np.reshape(mm[k, 0], shape), "max": np.reshape(mm[k, 1], shape)}
+  return out
+
+
+def collect_activation_statistics_batch(tensor_indices: Sequence[int], graph_info: qtyping.GraphInfo,
+                                        tensor_content_map: MutableMapping,
+                                        valid_float_range_min: float | None = None,
+                                        valid_float_range_max: float | None = None) -> list:
+  """[(name, content, {min, max, num_samples})] for the runtime tensors among `tensor_indices`
+  (constants are skipped), reduced in one batched launch."""
+  names, contents = [], []
+  for tid in tensor_indices:
+    tensor = graph_info.subgraph_tensors[tid]
+    if tfl_flatbuffer_utils.get_tensor_data(tensor, graph_info.buffers) is not None:
+      continue
+    name = tfl_flatbuffer_utils.get_tensor_name(tensor)
+    names.append(name)
+    contents.append(tensor_content_map[name])
+  qsvs = get_activation_min_max_batch(contents, valid_float_range_min, valid_float_range_max)
+  for c, q in zip(contents, qsvs):
+    q["num_samples"] = np.array(c.shape[0] if c.ndim > 0 else 1)
+  return list(zip(names, contents, qsvs))
+
+
 def collect_activation_tensor_statistics(tensor_idx: int, graph_info: qtyping.GraphInfo,
                                          tensor_content_map: MutableMapping,
                                          valid_float_range_min: float | None = None,

@@ -37,13 +37,10 @@ def calibrate(tfl_op, graph_info: qtyping.GraphInfo, tensor_content_map: Mutable
   del kwargs
   from ... import device
   op_qsvs = {}
-  for idx in common_quantize.get_tensor_indices_requiring_calibration(
-      tfl_op, graph_info, inputs_to_ignore, outputs_to_ignore):
-    got = common_quantize.collect_activation_tensor_statistics(
-        idx, graph_info, tensor_content_map, valid_range[0], valid_range[1])
-    if got is None:
-      continue
-    name, content, qsv = got
+  ids = common_quantize.get_tensor_indices_requiring_calibration(
+      tfl_op, graph_info, inputs_to_ignore, outputs_to_ignore)
+  for name, content, qsv in common_quantize.collect_activation_statistics_batch(
+      ids, graph_info, tensor_content_map, valid_range[0], valid_range[1]):
     x = hostio.to_device(content, np.float32)
     h = device.xtx(x, 2.0 / float(qsv["num_samples"]))
     qsv["hessian"] = h if keep_on_device else hostio.to_host(h)

@@ -143,14 +143,10 @@ def min_max_calibrate(tfl_op, graph_info: qtyping.GraphInfo, tensor_content_map,
   """{tensor name: {min, max, num_samples}} for every runtime tensor the op touches.
 
   Values outside the open interval `valid_range` are ignored (bf16 -inf padding
-  constants etc.); one device reduction per tensor.
+  constants etc.); one batched device launch for all the op's tensors.
   """
   del kwargs
-  op_qsvs = {}
-  for idx in common_quantize.get_tensor_indices_requiring_calibration(
-      tfl_op, graph_info, inputs_to_ignore, outputs_to_ignore):
-    got = common_quantize.collect_activation_tensor_statistics(
-        idx, graph_info, tensor_content_map, valid_range[0], valid_range[1])
-    if got is not None:
-      op_qsvs[got[0]] = got[2]
-  return op_qsvs
+  ids = common_quantize.get_tensor_indices_requiring_calibration(
+      tfl_op, graph_info, inputs_to_ignore, outputs_to_ignore)
+  return {name: qsv for name, _, qsv in common_quantize.collect_activation_statistics_batch(
+      ids, graph_info, tensor_content_map, valid_range[0], valid_range[1])}

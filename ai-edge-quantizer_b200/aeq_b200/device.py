@@ -112,8 +112,29 @@ def _minmax_ws(dev: torch.device) -> torch.Tensor:
   key = (dev.type, dev.index)
   if key not in _ws_cache:
     n = _lib.load().aeqb_minmax_workspace_bytes()
-    _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=dev)
+    _ws_cache[key] = torch.zeros(n, dtype=torch.uint8, device=dev)  # zeroed once; self-resetting
   return _ws_cache[key]
+
+
+def minmax_tensors(xs, lo: Optional[float] = None, hi: Optional[float] = None) -> torch.Tensor:
+  """[len(xs), 2] (min, max) of many tensors in one launch per 64 (aeqb_minmax_tensors_f32)."""
+  import ctypes
+  if not xs:
+    return torch.empty((0, 2), dtype=torch.float32)
+  dev = xs[0].device
+  keep = []
+  for x in xs:
+    if not x.is_cuda or x.dtype != torch.float32:
+      raise ValueError("expected float32 CUDA tensors")
+    keep.append(x.contiguous())
+  out = torch.empty((len(xs), 2), dtype=torch.float32, device=dev)
+  jobs = (_lib.MinmaxJob * len(xs))()
+  for i, x in enumerate(keep):
+    jobs[i] = _lib.MinmaxJob(_ptr(x), x.numel(), out[i].data_ptr())
+  _lib.call("aeqb_minmax_tensors_f32", ctypes.cast(jobs, ctypes.c_void_p), len(xs),
+            0.0 if lo is None else float(lo), 0.0 if hi is None else float(hi),
+            int(lo is not None), int(hi is not None), _ptr(_minmax_ws(dev)), _stream())
+  return out
 
 
 def minmax_tensor(x: torch.Tensor, lo: Optional[float] = None,

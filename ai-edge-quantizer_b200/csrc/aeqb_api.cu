@@ -226,17 +226,34 @@ int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, i
                     "aeqb_requant_blocks_batch_f32");
 }
 
-size_t aeqb_minmax_workspace_bytes(void) { return 8 * sizeof(int); }
+size_t aeqb_minmax_workspace_bytes(void) { return aeqb::minmax_workspace_bytes(); }
+
+int aeqb_minmax_tensors_f32(const aeqb_minmax_job* jobs, int64_t n_jobs, float lo, float hi,
+                            int use_lo, int use_hi, void* ws, void* stream) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad job list");
+  if (n_jobs > 0 && !ws) return fail("ws is NULL");
+  for (int64_t i0 = 0; i0 < n_jobs; i0 += aeqb::kMaxInlineJobs) {
+    aeqb::MinmaxBatch b{};
+    for (int64_t i = i0; i < n_jobs && i < i0 + aeqb::kMaxInlineJobs; ++i) {
+      if (jobs[i].n < 0) return fail("negative element count");
+      if (!jobs[i].out2) return fail("out2 is NULL");
+      if (jobs[i].n > 0 && !jobs[i].x) return fail("x is NULL");
+      aeqb::MinmaxJob& m = b.jobs[b.n_jobs++];
+      m.x = jobs[i].x; m.n = jobs[i].n; m.out2 = jobs[i].out2;
+    }
+    if (int rc = check(aeqb::launch_minmax_tensors(b, lo, hi, use_lo, use_hi, ws, sm_count(),
+                                                   static_cast<cudaStream_t>(stream)),
+                       "aeqb_minmax_tensors_f32"))
+      return rc;
+  }
+  return 0;
+}
 
 int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int use_lo, int use_hi,
                            float* out2, void* ws, void* stream) {
-  if (n < 0) return fail("negative element count");
-  if (!out2 || !ws) return fail("out2 / ws are NULL");
-  if (n > 0 && !x) return fail("x is NULL");
-  return check(aeqb::launch_minmax_tensor(x, n, lo, hi, use_lo, use_hi, out2,
-                                          static_cast<int*>(ws), sm_count(),
-                                          static_cast<cudaStream_t>(stream)),
-               "aeqb_minmax_tensor_f32");
+  aeqb_minmax_job j;
+  j.x = x; j.n = n; j.out2 = out2;
+  return aeqb_minmax_tensors_f32(&j, 1, lo, hi, use_lo, use_hi, ws, stream);
 }
 
 int aeqb_row_stats_f32(const float* x, int64_t rows, int64_t cols, float* mn, float* mx,

@@ -79,9 +79,23 @@ cudaError_t launch_requant_blocks_stream(const BlocksBatch& b, bool out_q, bool 
 cudaError_t launch_requant_blocks_generic(const BlocksJob& j, int block, int bits,
                                           cudaStream_t st);
 
-// Statistics (reduce.cu).  `ws` = 8 ints of device scratch.
-cudaError_t launch_minmax_tensor(const float* x, long long n, float lo, float hi, int use_lo,
-                                 int use_hi, float* out2, int* ws, int sm_count, cudaStream_t st);
+// Statistics (reduce.cu).
+struct MinmaxJob {
+  const float* x;
+  float* out2;                 // [min, max]
+  long long n;
+  long long nvec;              // launcher: aligned float4 count
+  long long tile0, tile_end;   // launcher
+  int head;                    // launcher: scalars before 16-byte alignment
+};
+struct MinmaxBatch {
+  MinmaxJob jobs[kMaxInlineJobs];
+  int n_jobs;
+  long long n_tiles;
+};
+size_t minmax_workspace_bytes();
+cudaError_t launch_minmax_tensors(MinmaxBatch& b, float lo, float hi, int use_lo, int use_hi,
+                                  void* ws, int sm_count, cudaStream_t st);
 cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn, float* mx,
                              float* sumsq, cudaStream_t st);
 cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,

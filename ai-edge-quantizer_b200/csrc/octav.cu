@@ -56,73 +56,122 @@ __device__ __forceinline__ bool is_close(float oldv, float newv) {
   return ((fabsf(__fsub_rn(oldv, newv)) <= tol) && fin) || (oldv == newv);
 }
 
-__device__ __forceinline__ void acc_elem(float v, float g, bool gzero, float& sum, int& cnt) {
-  const float a = fabsf(v);
-  if (a >= g) {  // false for NaN elements and NaN guesses
-    sum += a;
-    cnt += 1;
-  }
-  if (gzero && v == 0.0f) cnt += 1;  // x >= 0 and x <= -0 both hold for zeros
+// ---- branch-free inner loop on pre-conditioned magnitudes -------------------------------
+// At load time every element becomes a = |x| (NaN -> -1, which no guess >= 0 selects) and the
+// zeros of the group are counted once.  An iteration is then, per element pair,
+//   m = (a >= g) ? 1.0f : 0.0f   (FSET x2)    sum += a * m   (FFMA2)    cnt += m   (FADD2)
+// i.e. two issue slots per element on sm_100a's packed-fp32 pipe.  a * 1.0f and + 0.0f are exact,
+// so the arithmetic is the masked sum / count of the reference; counts stay exact in fp32 below
+// 2^24.  A NaN guess selects nothing (handled by the caller: the loop is skipped).
+__device__ __forceinline__ float mask_ge(float a, float g) {
+  float m;
+  asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(g));
+  return m;
+}
+
+__device__ __forceinline__ float condition(float x, int& zeros) {
+  zeros += (x == 0.0f);
+  return (x == x) ? fabsf(x) : -1.0f;
+}
+
+__device__ __forceinline__ void acc_pair(float a0, float a1, float g, float2& sum, float2& cnt) {
+  const float2 m = make_float2(mask_ge(a0, g), mask_ge(a1, g));
+  sum = __ffma2_rn(make_float2(a0, a1), m, sum);
+  cnt = __fadd2_rn(cnt, m);
 }
 
 // ------------------------------------------------------------------ rows
-// One CTA per row at a time (grid-stride over rows); thread t keeps float4
-// chunks t, t + T, ... of the row in registers (NV of them), so the row is read
-// from HBM exactly once and every iteration runs from registers.
-template <int NV, int THREADS>
+// One CTA per row at a time (grid-stride over rows); thread t keeps float4 chunks t, t + T, ...
+// of the row in registers (NV of them) and the NEXT row's chunks in flight, so HBM is read
+// exactly once and its latency hides behind the current row's iterations.  The recurrence
+// stops at its fixed point (new == old bitwise: later iterates are identical) and the rest of
+// the trace is filled, which removes most of the 10 iterations on real weights.
+template <int NV, int THREADS, bool PREFETCH>
 __global__ void __launch_bounds__(THREADS)
     octav_rows_trace(const float* __restrict__ x, long long rows, int cols, OctavConst k,
                      int iters, float* __restrict__ trace, unsigned* __restrict__ notclose) {
   constexpr int NW = THREADS / 32;
   __shared__ float s_sum[2][NW];
-  __shared__ int s_cnt[2][NW];
+  __shared__ float s_cnt[2][NW];
+  __shared__ int s_zero[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nvec = cols >> 2;
   unsigned my_mask = 0;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+  float4 nxt[NV];
+  auto load_row = [&](long long row) {
     const float4* p = reinterpret_cast<const float4*>(x + row * cols);
-    float4 v[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = j * THREADS + tid;
-      v[j] = i < nvec ? __ldg(p + i) : make_float4(NAN, NAN, NAN, NAN);
+      nxt[j] = (row < rows && i < nvec) ? __ldg(p + i) : make_float4(NAN, NAN, NAN, NAN);
     }
+  };
+  load_row(blockIdx.x);
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    float4 a[NV];
+    int zeros = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      a[j].x = condition(nxt[j].x, zeros); a[j].y = condition(nxt[j].y, zeros);
+      a[j].z = condition(nxt[j].z, zeros); a[j].w = condition(nxt[j].w, zeros);
+    }
+    if (PREFETCH) load_row(row + gridDim.x);  // in flight during the iterations below
+    zeros = __reduce_add_sync(0xffffffffu, zeros);
+    if (lane == 0) s_zero[warp] = zeros;
+    __syncthreads();
+    int row_zeros = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) row_zeros += s_zero[w];
+
     float g = 1.0f;
-    for (int it = 0; it < iters; ++it) {
-      float sum = 0.0f;
-      int cnt = 0;
-      const bool gz = g == 0.0f;
+    int it = 0;
+    for (; it < iters; ++it) {
+      float2 sum = make_float2(0.0f, 0.0f), cnt = make_float2(0.0f, 0.0f);
+      if (g == g) {  // a NaN guess selects nothing
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        acc_elem(v[j].x, g, gz, sum, cnt);
-        acc_elem(v[j].y, g, gz, sum, cnt);
-        acc_elem(v[j].z, g, gz, sum, cnt);
-        acc_elem(v[j].w, g, gz, sum, cnt);
+        for (int j = 0; j < NV; ++j) {
+          acc_pair(a[j].x, a[j].y, g, sum, cnt);
+          acc_pair(a[j].z, a[j].w, g, sum, cnt);
+        }
       }
+      float ts = sum.x + sum.y, tc = cnt.x + cnt.y;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      for (int o = 16; o > 0; o >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tc += __shfl_xor_sync(0xffffffffu, tc, o);
+      }
       const int b = it & 1;
       if (lane == 0) {
-        s_sum[b][warp] = sum;
-        s_cnt[b][warp] = cnt;
+        s_sum[b][warp] = ts;
+        s_cnt[b][warp] = tc;
       }
       __syncthreads();  // double-buffered: one barrier per iteration
-      float tsum = 0.0f;
-      int tcnt = 0;
+      float rs = 0.0f, rc = 0.0f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
-        tsum += s_sum[b][w];
-        tcnt += s_cnt[b][w];
+        rs += s_sum[b][w];
+        rc += s_cnt[b][w];
       }
-      const float ng = octav_update(tsum, tcnt, k);
+      const int cnt_i = static_cast<int>(rc) + (g == 0.0f ? row_zeros : 0);
+      const float ng = octav_update(rs, cnt_i, k);
       if (tid == 0) {
         trace[static_cast<long long>(it) * rows + row] = ng;
         if (!is_close(g, ng)) my_mask |= 1u << it;
       }
+      const bool fixed = (ng == g) || (ng != ng && g != g);
       g = ng;
+      if (fixed) { ++it; break; }  // CTA-uniform: every thread holds the same g
     }
-    __syncthreads();  // s_* of parity (iters-1)&1 may be rewritten by the next row's first iterations
+    if (tid == 0) {
+      // Past a fixed point every iterate equals g; np.isclose(g, g) holds unless g is NaN / inf-inf.
+      const bool self_close = is_close(g, g);
+      for (int r = it; r < iters; ++r) {
+        trace[static_cast<long long>(r) * rows + row] = g;
+        if (!self_close) my_mask |= 1u << r;
+      }
+    }
+    __syncthreads();  // s_* are rewritten by the next row
+    if (!PREFETCH) load_row(row + gridDim.x);
   }
   if (tid == 0 && my_mask) atomicOr(notclose, my_mask);
 }
@@ -182,64 +231,91 @@ __global__ void __launch_bounds__(1024)
 }
 
 // ------------------------------------------------------------------ blocks
-// Each lane owns 8 consecutive floats; BLOCK/8 lanes share a group and reduce
-// with xor-shuffles, so a group's whole trajectory is computed in registers.
+// A warp owns 1024 consecutive floats at a time = 32 segments of 32; the tile is loaded with
+// coalesced 128-bit loads, transposed through a padded shared-memory tile (row stride 33: both
+// the scatter and the gather are bank-conflict free) so that lane l holds segment l in
+// registers, conditioned once.  A block is BLOCK/32 adjacent lanes; its iterations run from
+// registers with xor-shuffles across those lanes (none at BLOCK == 32).
 template <int BLOCK>
 __global__ void __launch_bounds__(256)
     octav_blocks_trace(const float* __restrict__ x, long long n, OctavConst k, int iters,
                        float* __restrict__ trace, unsigned* __restrict__ notclose) {
-  constexpr int LPB = BLOCK / 8;
+  constexpr int LPB = BLOCK / 32;
+  __shared__ float s_t[8][32 * 33];
   __shared__ unsigned s_mask;
   if (threadIdx.x == 0) s_mask = 0;
   __syncthreads();
-  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* t = s_t[warp];
   const long long nblk = n / BLOCK;
+  const long long nwt = (n + 1023) / 1024;  // warp tiles
   const bool aligned = reinterpret_cast<uintptr_t>(x) % 16 == 0;
-  const int lane = threadIdx.x & 31;
   unsigned my_mask = 0;
-  // Warp-uniform trip count (full-mask shuffles inside); lanes past the end hold NaN,
-  // which no comparison selects.  n is a multiple of BLOCK, so a group is valid as a whole.
-  for (long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + (threadIdx.x - lane);
-       t0 * 8 < n; t0 += nthreads) {
-    const long long e = (t0 + lane) * 8;
-    const bool valid = e < n;
-    float v[8];
-    if (!valid) {
+  for (long long wt = static_cast<long long>(blockIdx.x) * 8 + warp; wt < nwt;
+       wt += static_cast<long long>(gridDim.x) * 8) {
+    const long long e0 = wt * 1024;
+    // ---- coalesced load + scatter into the padded tile
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = NAN;
-    } else if (aligned) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(x + e));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(x + e + 4));
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = x[e + j];
+    for (int i = 0; i < 8; ++i) {
+      const int f = i * 32 + lane;               // float4 index inside the tile
+      const long long e = e0 + 4LL * f;
+      float4 v = make_float4(NAN, NAN, NAN, NAN);
+      if (e + 3 < n) {
+        if (aligned) v = __ldg(reinterpret_cast<const float4*>(x + e));
+        else v = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
+      }
+      const int seg = f >> 3, pos = (f & 7) * 4;
+      float* d = t + seg * 33 + pos;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
-    const long long blk = e / BLOCK;
-    const bool writer = valid && (lane & (LPB - 1)) == 0;
-    float g = 1.0f;
-    for (int it = 0; it < iters; ++it) {
-      float sum = 0.0f;
-      int cnt = 0;
-      const bool gz = g == 0.0f;
+    __syncwarp();
+    float a[32];
+    int zeros = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc_elem(v[j], g, gz, sum, cnt);
+    for (int p = 0; p < 32; ++p) a[p] = condition(t[lane * 33 + p], zeros);
+    __syncwarp();
+#pragma unroll
+    for (int o = 1; o < LPB; o <<= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    const long long seg_e = e0 + 32LL * lane;    // first element of this lane's segment
+    const bool valid = seg_e < n;
+    const long long blk = seg_e / BLOCK;
+    const bool writer = valid && (lane & (LPB - 1)) == 0;
+
+    float g = 1.0f;
+    int it = 0;
+    for (; it < iters; ++it) {
+      float2 sum = make_float2(0.0f, 0.0f), cnt = make_float2(0.0f, 0.0f);
+      if (g == g) {
+#pragma unroll
+        for (int p = 0; p < 32; p += 2) acc_pair(a[p], a[p + 1], g, sum, cnt);
+      }
+      float ts = sum.x + sum.y, tc = cnt.x + cnt.y;
 #pragma unroll
       for (int o = 1; o < LPB; o <<= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tc += __shfl_xor_sync(0xffffffffu, tc, o);
       }
-      const float ng = octav_update(sum, cnt, k);
+      const int cnt_i = static_cast<int>(tc) + (g == 0.0f ? zeros : 0);
+      const float ng = octav_update(ts, cnt_i, k);
       if (writer) {
         trace[static_cast<long long>(it) * nblk + blk] = ng;
         if (!is_close(g, ng)) my_mask |= 1u << it;
       }
+      const bool fixed = (ng == g) || (ng != ng && g != g);
       g = ng;
+      // leave only when every block of the warp sits at its fixed point (shuffles need all lanes)
+      if (__all_sync(0xffffffffu, fixed)) { ++it; break; }
+    }
+    if (writer) {
+      const bool self_close = is_close(g, g);
+      for (int r = it; r < iters; ++r) {
+        trace[static_cast<long long>(r) * nblk + blk] = g;
+        if (!self_close) my_mask |= 1u << r;
+      }
     }
   }
   my_mask = __reduce_or_sync(0xffffffffu, my_mask);
-  if ((threadIdx.x & 31) == 0 && my_mask) atomicOr(&s_mask, my_mask);
+  if (lane == 0 && my_mask) atomicOr(&s_mask, my_mask);
   __syncthreads();
   if (threadIdx.x == 0 && s_mask) atomicOr(notclose, s_mask);
 }
@@ -272,14 +348,16 @@ OctavConst make_const(int bits, float divisor, long long n) {
   return k;
 }
 
-template <int NV>
+template <int NV, int T>
 void launch_rows_nv(const float* x, long long rows, int cols, const OctavConst& k, int iters,
                     float* trace, unsigned* notclose, int sm_count, cudaStream_t st) {
-  constexpr int T = 256;
-  long long grid = static_cast<long long>(sm_count) * (NV <= 4 ? 6 : (NV <= 8 ? 4 : 2));
+  // Measured on B200 (tools/ktime.py): insensitive to 4..16 CTAs per SM and to the prefetch; the
+  // kernel is issue-bound (IPC 2.45 of 4), see profiles/.
+  const int per_sm = (2048 / T) < 8 ? (2048 / T) : 8;
+  long long grid = static_cast<long long>(sm_count) * per_sm;
   if (grid > rows) grid = rows;
-  octav_rows_trace<NV, T><<<static_cast<unsigned>(grid), T, 0, st>>>(x, rows, cols, k, iters, trace,
-                                                                      notclose);
+  octav_rows_trace<NV, T, false><<<static_cast<unsigned>(grid), T, 0, st>>>(x, rows, cols, k, iters,
+                                                                             trace, notclose);
 }
 
 }  // namespace
@@ -303,12 +381,13 @@ cudaError_t launch_octav_rows(const float* x, long long rows, long long cols, in
                    cols <= 16384;
   if (vec) {
     const int c = static_cast<int>(cols);
-    const int nv = (c / 4 + 255) / 256;  // float4 per thread
-    if (nv <= 1) launch_rows_nv<1>(x, rows, c, k, iters, trace, notclose, sm_count, st);
-    else if (nv <= 2) launch_rows_nv<2>(x, rows, c, k, iters, trace, notclose, sm_count, st);
-    else if (nv <= 4) launch_rows_nv<4>(x, rows, c, k, iters, trace, notclose, sm_count, st);
-    else if (nv <= 8) launch_rows_nv<8>(x, rows, c, k, iters, trace, notclose, sm_count, st);
-    else launch_rows_nv<16>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    const int v4 = c / 4;  // float4 per row; <= 8 per thread, thread count grows with the row
+    if (v4 <= 128) launch_rows_nv<1, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 256) launch_rows_nv<2, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 512) launch_rows_nv<4, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 1024) launch_rows_nv<8, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 2048) launch_rows_nv<8, 256>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else launch_rows_nv<8, 512>(x, rows, c, k, iters, trace, notclose, sm_count, st);
   } else {
     long long grid = static_cast<long long>(sm_count) * 2;
     if (grid > rows) grid = rows;
@@ -333,8 +412,8 @@ cudaError_t launch_octav_blocks(const float* x, long long n, int block, int bits
   cudaError_t e = cudaMemsetAsync(notclose, 0, 256, st);
   if (e != cudaSuccess) return e;
   const OctavConst k = make_const(bits, divisor, block);
-  long long grid = (n / 8 + 255) / 256;
-  const long long cap = static_cast<long long>(sm_count) * 8;
+  long long grid = ((n + 1023) / 1024 + 7) / 8;  // 8 warp tiles per CTA pass
+  const long long cap = static_cast<long long>(sm_count) * 6;
   if (grid > cap) grid = cap;
   const unsigned g = static_cast<unsigned>(grid);
   switch (block) {

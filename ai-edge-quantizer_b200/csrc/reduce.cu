@@ -23,86 +23,168 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
-// ---------------------------------------------------------------- whole tensor
-// ws layout (ints): 0 fmin_ord, 1 fmax_ord, 2 rmin_ord, 3 rmax_ord, 4 nan flag
+// ---------------------------------------------------------------- whole tensors, batched
+// ONE launch reduces up to kMaxInlineJobs tensors (a calibration step's activations):
+// the tensors form one stream of 16 KiB tiles, a persistent CTA takes every gridDim-th
+// tile with four 128-bit loads in flight per thread, keeps (filtered min, filtered max,
+// raw min, raw max, NaN seen) in registers while it stays inside one tensor, and flushes a
+// block-reduced partial into its own slot ws[cta][job] when it moves on.  No atomics on
+// shared addresses (9.5 k same-address atomics cost more than the 64 MiB read); the last
+// CTA to finish (one counter) folds the slots and applies the reference's raw fallback.
+constexpr int kMmThreads = 256;
+constexpr int kMmTileVec = kMmThreads * 4;  // float4 per tile
+constexpr int kMmMaxGrid = 2048;
+
 struct TensorAcc {
   float fmin, fmax;  // filtered (x > lo / x < hi); NaN never passes a comparison
-  float rmin, rmax;  // raw, NaN tracked separately
-  int nan;
+  float rmin, rmax;  // raw, NaN-propagating (np.min / np.max semantics)
 };
+
+__device__ __forceinline__ void acc_reset(TensorAcc& a) {
+  a.fmin = INFINITY; a.fmax = -INFINITY; a.rmin = INFINITY; a.rmax = -INFINITY;
+}
 
 __device__ __forceinline__ void acc1(TensorAcc& a, float v, float lo, float hi) {
   if (v > lo) a.fmin = fminf(a.fmin, v);
   if (v < hi) a.fmax = fmaxf(a.fmax, v);
-  a.rmin = fminf(a.rmin, v);
-  a.rmax = fmaxf(a.rmax, v);
-  a.nan |= (v != v);
+  a.rmin = min_nan(a.rmin, v);
+  a.rmax = max_nan(a.rmax, v);
 }
 
-__global__ void minmax_tensor_init(int* ws) {
-  ws[0] = f2ord(INFINITY);
-  ws[1] = f2ord(-INFINITY);
-  ws[2] = f2ord(INFINITY);
-  ws[3] = f2ord(-INFINITY);
-  ws[4] = 0;
+// Sixteen elements at ~2 instructions each: NaN-propagating min / max of the group first; only
+// when the group touches the filter bounds (or holds a NaN) does the per-element path run.
+__device__ __forceinline__ void acc16(TensorAcc& a, const float4 (&v)[4], float lo, float hi) {
+  float mn = min_nan(min_nan(v[0].x, v[0].y), min_nan(v[0].z, v[0].w));
+  float mx = max_nan(max_nan(v[0].x, v[0].y), max_nan(v[0].z, v[0].w));
+#pragma unroll
+  for (int u = 1; u < 4; ++u) {
+    mn = min_nan(mn, min_nan(min_nan(v[u].x, v[u].y), min_nan(v[u].z, v[u].w)));
+    mx = max_nan(mx, max_nan(max_nan(v[u].x, v[u].y), max_nan(v[u].z, v[u].w)));
+  }
+  if (mn > lo && mx < hi) {  // false when mn / mx is NaN
+    a.fmin = fminf(a.fmin, mn);
+    a.fmax = fmaxf(a.fmax, mx);
+    a.rmin = min_nan(a.rmin, mn);
+    a.rmax = max_nan(a.rmax, mx);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc1(a, v[u].x, lo, hi); acc1(a, v[u].y, lo, hi); acc1(a, v[u].z, lo, hi); acc1(a, v[u].w, lo, hi);
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256)
-    minmax_tensor_kernel(const float* __restrict__ x, long long n, float lo, float hi, int* ws) {
-  TensorAcc a{INFINITY, -INFINITY, INFINITY, -INFINITY, 0};
-  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-  // scalar head until 16-byte alignment, vector body, scalar tail
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
-  long long head = ((16 - (addr & 15)) & 15) / 4;
-  if (head > n) head = n;
-  const long long nvec = (n - head) / 4;
-  const float4* xv = reinterpret_cast<const float4*>(x + head);
-  for (long long i = tid; i < head; i += nthreads) acc1(a, x[i], lo, hi);
-  long long i = tid;
-  for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {
-    const float4 v0 = ldg_stream(xv + i);
-    const float4 v1 = ldg_stream(xv + i + nthreads);
-    const float4 v2 = ldg_stream(xv + i + 2 * nthreads);
-    const float4 v3 = ldg_stream(xv + i + 3 * nthreads);
-    acc1(a, v0.x, lo, hi); acc1(a, v0.y, lo, hi); acc1(a, v0.z, lo, hi); acc1(a, v0.w, lo, hi);
-    acc1(a, v1.x, lo, hi); acc1(a, v1.y, lo, hi); acc1(a, v1.z, lo, hi); acc1(a, v1.w, lo, hi);
-    acc1(a, v2.x, lo, hi); acc1(a, v2.y, lo, hi); acc1(a, v2.z, lo, hi); acc1(a, v2.w, lo, hi);
-    acc1(a, v3.x, lo, hi); acc1(a, v3.y, lo, hi); acc1(a, v3.z, lo, hi); acc1(a, v3.w, lo, hi);
-  }
-  for (; i < nvec; i += nthreads) {
-    const float4 v = ldg_stream(xv + i);
-    acc1(a, v.x, lo, hi); acc1(a, v.y, lo, hi); acc1(a, v.z, lo, hi); acc1(a, v.w, lo, hi);
-  }
-  for (long long j = head + nvec * 4 + tid; j < n; j += nthreads) acc1(a, x[j], lo, hi);
+__device__ __forceinline__ void acc_merge(TensorAcc& a, const TensorAcc& b) {
+  a.fmin = fminf(a.fmin, b.fmin); a.fmax = fmaxf(a.fmax, b.fmax);
+  a.rmin = min_nan(a.rmin, b.rmin); a.rmax = max_nan(a.rmax, b.rmax);
+}
 
+__device__ __forceinline__ TensorAcc acc_warp(TensorAcc a) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    a.fmin = fminf(a.fmin, __shfl_xor_sync(0xffffffffu, a.fmin, o));
-    a.fmax = fmaxf(a.fmax, __shfl_xor_sync(0xffffffffu, a.fmax, o));
-    a.rmin = fminf(a.rmin, __shfl_xor_sync(0xffffffffu, a.rmin, o));
-    a.rmax = fmaxf(a.rmax, __shfl_xor_sync(0xffffffffu, a.rmax, o));
-    a.nan |= __shfl_xor_sync(0xffffffffu, a.nan, o);
+    TensorAcc b;
+    b.fmin = __shfl_xor_sync(0xffffffffu, a.fmin, o);
+    b.fmax = __shfl_xor_sync(0xffffffffu, a.fmax, o);
+    b.rmin = __shfl_xor_sync(0xffffffffu, a.rmin, o);
+    b.rmax = __shfl_xor_sync(0xffffffffu, a.rmax, o);
+    acc_merge(a, b);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&ws[0], f2ord(a.fmin));
-    atomicMax(&ws[1], f2ord(a.fmax));
-    atomicMin(&ws[2], f2ord(a.rmin));
-    atomicMax(&ws[3], f2ord(a.rmax));
-    if (a.nan) atomicOr(&ws[4], 1);
-  }
+  return a;
 }
 
-// common_quantize.py:1386-1408: filtered value unless nothing passed the filter
-// (then the raw, NaN-propagating np.min / np.max).
-__global__ void minmax_tensor_final(const int* ws, int use_lo, int use_hi, long long n,
-                                    float* out) {
-  const float fmin = ord2f(ws[0]), fmax = ord2f(ws[1]);
-  const float rmin = ws[4] ? NAN : ord2f(ws[2]);
-  const float rmax = ws[4] ? NAN : ord2f(ws[3]);
-  out[0] = (use_lo && fmin != INFINITY) ? fmin : rmin;
-  out[1] = (use_hi && fmax != -INFINITY) ? fmax : rmax;
-  (void)n;
+// ws: [0] finished-CTA counter (zero before the first launch; the kernel re-zeroes it),
+//     then slots[grid][n_jobs] of 4 floats.
+__global__ void __launch_bounds__(kMmThreads)
+    minmax_tensors_kernel(const __grid_constant__ MinmaxBatch b, float lo, float hi, int use_lo,
+                          int use_hi, float* __restrict__ ws) {
+  __shared__ TensorAcc s_w[kMmThreads / 32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* slots = ws + 8 + static_cast<size_t>(blockIdx.x) * b.n_jobs * 4;
+  for (int j = tid; j < b.n_jobs; j += kMmThreads) {
+    float* s = slots + j * 4;
+    s[0] = INFINITY; s[1] = -INFINITY; s[2] = INFINITY; s[3] = -INFINITY;
+  }
+  __syncthreads();
+
+  TensorAcc a;
+  acc_reset(a);
+  int j = 0;
+  bool dirty = false;
+  auto flush = [&](int job) {  // block-reduce `a` into this CTA's slot of `job`
+    const TensorAcc w = acc_warp(a);
+    if (lane == 0) s_w[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+      TensorAcc t = s_w[0];
+      for (int k = 1; k < kMmThreads / 32; ++k) acc_merge(t, s_w[k]);
+      float* s = slots + job * 4;
+      s[0] = t.fmin; s[1] = t.fmax; s[2] = t.rmin; s[3] = t.rmax;
+    }
+    __syncthreads();
+    acc_reset(a);
+  };
+  for (long long tile = blockIdx.x; tile < b.n_tiles; tile += gridDim.x) {
+    while (tile >= b.jobs[j].tile_end) {
+      if (dirty) { flush(j); dirty = false; }
+      ++j;
+    }
+    const MinmaxJob& job = b.jobs[j];
+    const long long t = tile - job.tile0;
+    const float4* xv = reinterpret_cast<const float4*>(job.x + job.head);
+    const long long v0 = t * kMmTileVec;
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = v0 + u * kMmThreads + tid;
+      v[u] = i < job.nvec ? ldg_stream(xv + i) : make_float4(NAN, NAN, NAN, NAN);
+    }
+    if (v0 + kMmTileVec <= job.nvec) {
+      acc16(a, v, lo, hi);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = v0 + u * kMmThreads + tid;
+        if (i < job.nvec) {
+          acc1(a, v[u].x, lo, hi); acc1(a, v[u].y, lo, hi); acc1(a, v[u].z, lo, hi); acc1(a, v[u].w, lo, hi);
+        }
+      }
+    }
+    if (t == 0) {  // unaligned head and the < 4-element tail ride along with the first tile
+      if (tid < job.head) acc1(a, job.x[tid], lo, hi);
+      const long long tail0 = job.head + job.nvec * 4;
+      if (tail0 + tid < job.n && tid < 4) acc1(a, job.x[tail0 + tid], lo, hi);
+    }
+    dirty = true;
+  }
+  if (dirty) flush(j);
+
+  // ---- last CTA folds every slot
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(reinterpret_cast<int*>(ws), 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int job = warp; job < b.n_jobs; job += kMmThreads / 32) {
+    TensorAcc t;
+    acc_reset(t);
+    for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) {
+      const float4 o4 = __ldcg(reinterpret_cast<const float4*>(
+          ws + 8 + (static_cast<size_t>(c) * b.n_jobs + job) * 4));
+      TensorAcc o;
+      o.fmin = o4.x; o.fmax = o4.y; o.rmin = o4.z; o.rmax = o4.w;
+      acc_merge(t, o);
+    }
+    t = acc_warp(t);
+    if (lane == 0) {
+      // common_quantize.py:1386-1408: the filtered value unless nothing passed the filter, then
+      // the raw NaN-propagating np.min / np.max.  An empty tensor keeps +-inf.
+      float* out = b.jobs[job].out2;
+      out[0] = (use_lo && t.fmin != INFINITY) ? t.fmin : t.rmin;
+      out[1] = (use_hi && t.fmax != -INFINITY) ? t.fmax : t.rmax;
+    }
+  }
+  if (tid == 0) *reinterpret_cast<int*>(ws) = 0;  // ready for the next launch on this stream
 }
 
 // ---------------------------------------------------------------- per row
@@ -221,20 +303,36 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-cudaError_t launch_minmax_tensor(const float* x, long long n, float lo, float hi, int use_lo,
-                                 int use_hi, float* out2, int* ws, int sm_count,
-                                 cudaStream_t st) {
-  minmax_tensor_init<<<1, 1, 0, st>>>(ws);
-  if (n > 0) {
-    long long blocks = (n / 4 + 255) / 256;
-    const long long cap = static_cast<long long>(sm_count) * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    minmax_tensor_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        x, n, use_lo ? lo : -INFINITY, use_hi ? hi : INFINITY, ws);
+size_t minmax_workspace_bytes() {
+  return 32 + static_cast<size_t>(kMmMaxGrid) * kMaxInlineJobs * 4 * sizeof(float);
+}
+
+// jobs: x / n / out2 filled by the caller; the rest is derived here.
+cudaError_t launch_minmax_tensors(MinmaxBatch& b, float lo, float hi, int use_lo, int use_hi,
+                                  void* ws, int sm_count, cudaStream_t st) {
+  if (b.n_jobs <= 0) return cudaSuccess;
+  long long tiles = 0;
+  for (int j = 0; j < b.n_jobs; ++j) {
+    MinmaxJob& m = b.jobs[j];
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m.x);
+    long long head = (addr % 4 == 0) ? static_cast<long long>(((16 - (addr & 15)) & 15) / 4) : m.n;
+    if (head > m.n) head = m.n;
+    m.head = static_cast<int>(head);
+    m.nvec = (m.n - head) / 4;
+    if (addr % 4 != 0) return cudaErrorMisalignedAddress;
+    long long nt = (m.nvec + kMmTileVec - 1) / kMmTileVec;
+    if (nt < 1) nt = 1;  // head / tail / empty tensors still get one tile (writes +-inf when empty)
+    m.tile0 = tiles;
+    tiles += nt;
+    m.tile_end = tiles;
   }
-  minmax_tensor_final<<<1, 1, 0, st>>>(ws, use_lo, use_hi, n, out2);
-  return count_launch(n > 0 ? 3 : 2);
+  b.n_tiles = tiles;
+  long long grid = static_cast<long long>(sm_count) * 8;
+  if (grid > kMmMaxGrid) grid = kMmMaxGrid;
+  if (grid > tiles) grid = tiles;
+  minmax_tensors_kernel<<<static_cast<unsigned>(grid), kMmThreads, 0, st>>>(
+      b, use_lo ? lo : -INFINITY, use_hi ? hi : INFINITY, use_lo, use_hi, static_cast<float*>(ws));
+  return count_launch();
 }
 
 cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn, float* mx,

@@ -137,9 +137,20 @@ AEQB_API void aeqb_host_release(void);
  * use_lo == 0), out2[1] = max{x : x < hi} likewise.  Replaces
  * common_quantize.get_activation_min_max (common_quantize.py:1362-1413), the
  * reduction inside naive_min_max_quantize.min_max_calibrate (:181-226) and
- * gptq.calibrate's min/max (gptq.py:84-98).  ws: aeqb_minmax_workspace_bytes()
- * bytes of device scratch. */
+ * gptq.calibrate's min/max (gptq.py:84-98).
+ *   The batched form reduces all the activation tensors of one calibration step
+ *   (calibrator.py:545-582 visits them one by one) in ONE launch per 64 tensors.
+ *   ws: aeqb_minmax_workspace_bytes() bytes of device scratch, ZEROED before its
+ *   first use (the kernel leaves it ready for the next call); one ws per stream. */
+typedef struct aeqb_minmax_job {
+  const float* x; /* device, 4-byte aligned */
+  int64_t n;
+  float* out2;    /* device [2] */
+} aeqb_minmax_job;
+
 AEQB_API size_t aeqb_minmax_workspace_bytes(void);
+AEQB_API int aeqb_minmax_tensors_f32(const aeqb_minmax_job* jobs, int64_t n_jobs, float lo, float hi,
+                                     int use_lo, int use_hi, void* ws, void* stream);
 AEQB_API int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int use_lo,
                                     int use_hi, float* out2, void* ws, void* stream);
 

@@ -132,3 +132,33 @@ def test_scale_zp_kernel_matches_oracle(cuda):
             ozp, osc = O.scale_zp(mn, mx, bits, sym, blockwise, c)
           np.testing.assert_array_equal(sc.cpu().numpy(), osc)
           np.testing.assert_array_equal(zp.cpu().numpy().astype(ozp.dtype), ozp)  # uqt:585 cast wraps
+
+
+def test_minmax_tensors_batched(cuda):
+  """70 ragged tensors (> 64: two launches), unaligned views, NaN / inf / all-filtered cases,
+  twice in a row (the workspace resets itself)."""
+  import torch
+  from aeq_b200 import device
+  rng = np.random.default_rng(11)
+  sizes = [1, 2, 3, 5, 1023, 1024, 1025, 4096, 4097, 70000, 262144 + 3] * 6 + [8, 16, 100, 9]
+  arrs = [rng.standard_normal(n).astype(np.float32) * (1 + i % 5) for i, n in enumerate(sizes)]
+  arrs[3][1] = np.nan
+  arrs[9][5] = np.inf
+  arrs[10][7] = -np.inf
+  arrs[12][:] = 3.2e38            # everything filtered -> raw fallback
+  arrs[20][0] = 3.39e38
+  big = torch.from_numpy(np.concatenate([np.zeros(1, np.float32)] + arrs)).to(cuda)
+  xs, off = [], 1                 # views at odd offsets: not 16-byte aligned
+  for a in arrs:
+    xs.append(big[off:off + a.size])
+    off += a.size
+  for _ in range(2):
+    got = device.minmax_tensors(xs, -3e38, 3e38).cpu().numpy()
+    for a, g in zip(arrs, got):
+      with np.errstate(all="ignore"):
+        mn, mx = O.activation_minmax(a)
+      np.testing.assert_array_equal(g, np.array([mn.item(), mx.item()], np.float32))
+  raw = device.minmax_tensors(xs).cpu().numpy()
+  for a, g in zip(arrs, raw):
+    with np.errstate(all="ignore"):
+      np.testing.assert_array_equal(g, np.array([a.min(), a.max()], np.float32))
