@@ -136,3 +136,45 @@ def install(reference_algorithm_manager, algorithms=None) -> list[str]:
       mod.get_tensor_quant_params = adapted
     bound.append(key)
   return bound
+
+
+def prefetch(params_generator, model_recipe_manager) -> dict:
+  """Quantises all min-max weights of the reference ParamsGenerator's model in a few batched
+  launches and fills its `(buffer, config)` cache; call it right before
+  `params_generator.generate_quantization_parameters(model_recipe_manager, ...)`.
+
+  Mirrors the reference's own walk (params_generator.py:110-158): same op keys, scopes, recipe
+  lookups and composite / NO_QUANTIZE skipping, using the reference's modules as found in the
+  generator's module namespace.  The per-op materialisers then hit the cache
+  (common_utils.py:260-264).
+  """
+  import sys
+  from . import prefetch as _prefetch
+  pg = params_generator
+  mod = sys.modules[type(pg).__module__]
+  fu, am, rq = mod.tfl_flatbuffer_utils, mod.algorithm_manager, mod.qtyping
+  policy = getattr(mod, "policy", None)
+  model = pg.float_model
+  op_codes = model.operatorCodes
+  min_max = am.AlgorithmName.MIN_MAX_UNIFORM_QUANT
+  items, skip_subgraphs = [], set()
+  for sg_ind, subgraph in enumerate(model.subgraphs):
+    graph_info = rq.GraphInfo(subgraph.tensors, model.buffers)
+    for op_id, op in enumerate(subgraph.operators):
+      code = op_codes[op.opcodeIndex].builtinCode
+      if code not in fu.TFL_OP_CODE_TO_NAME:
+        continue
+      op_key = fu.TFL_OP_CODE_TO_NAME[code]
+      algorithm_name, op_config = model_recipe_manager.get_quantization_configs(
+          op_key, fu.get_op_scope(op, subgraph.tensors))
+      if sg_ind in skip_subgraphs or (policy is not None and policy.is_non_quantizable_composite_op(op)):
+        algorithm_name = am.AlgorithmName.NO_QUANTIZE
+      if algorithm_name == am.AlgorithmName.NO_QUANTIZE:
+        skip_subgraphs.update(fu.get_op_side_effect_subgraphs(op))
+        continue
+      if algorithm_name != min_max or op_config.weight_tensor_config is None:
+        continue
+      items.append((rq.OpInfo(op, op_key, op_id, op_config), graph_info))
+  return _prefetch.prefetch_weights(
+      items, pg._tensor_quant_params_cache,  # pylint: disable=protected-access
+      make_params=lambda **kw: rq.UniformQuantParams(**kw), get_tensor_data=fu.get_tensor_data)

@@ -71,7 +71,7 @@ struct RowsOpts { int bits, symmetric; };
 // class (one persistent launch each), the rest go through the generic kernel.
 int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who) {
   const int sms = sm_count();
-  for (int klass = 1; klass <= 2; ++klass) {
+  for (int klass = 1; klass <= 3; ++klass) {
     aeqb::RowsBatch b{};
     b.bits = o.bits; b.symmetric = o.symmetric;
     auto flush = [&]() -> int {
@@ -356,9 +356,11 @@ int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp, int keep_d
                "aeqb_hessian_inverse_f64");
 }
 
+size_t aeqb_gptq_workspace_bytes(int64_t rows) { return rows > 0 ? aeqb::gptq_workspace_bytes(rows) : 0; }
+
 int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
                            const float* scale, const int32_t* zp, int64_t scale_cols, int block,
-                           int bits, int symmetric, int blocksize, int8_t* q, void* stream) {
+                           int bits, int symmetric, int blocksize, int8_t* q, void* ws, void* stream) {
   if (rows < 0 || k < 0 || rows > 0x7fffffff || k > 0x7fffffff)
     return fail("bad shape [%lld, %lld]", (long long)rows, (long long)k);
   if (blocksize != 64) return fail("GPTQ blocksize must be 64 (gptq.py:136), got %d", blocksize);
@@ -368,10 +370,10 @@ int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* 
   if (block && (k % block || scale_cols != k / block))
     return fail("blockwise scales must be [rows, k / block]");
   if (!block && scale_cols != 0 && scale_cols != 1) return fail("scale_cols must be 0 or 1 without blocks");
-  if (rows * k > 0 && (!w_work || !hinv || !scale || !q)) return fail("w_work / hinv / scale / q are NULL");
+  if (rows * k > 0 && (!w_work || !hinv || !scale || !q || !ws)) return fail("w_work / hinv / scale / q / ws are NULL");
   return check(aeqb::launch_gptq_quantize(w_work, rows, k, hinv, scale, zp,
                                           static_cast<int>(scale_cols), block, bits,
-                                          symmetric ? 1 : 0, q, static_cast<cudaStream_t>(stream)),
+                                          symmetric ? 1 : 0, q, ws, static_cast<cudaStream_t>(stream)),
                "aeqb_gptq_quantize_f32");
 }
 

@@ -45,7 +45,7 @@ struct RowsBatch {
   int symmetric;
   long long n_tiles;
 };
-// 0: generic kernel, 1: 32 KiB stages (rows <= 8192 floats), 2: 64 KiB stages.
+// 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
 int rows_job_class(const RowsJob& j, int bits);
 int rows_job_rows_per_tile(const RowsJob& j, int klass);
 cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count, cudaStream_t st);
@@ -129,9 +129,10 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
                                    cudaStream_t st);
 cudaError_t launch_weighted_mean_f64(const double* a, double wa, const double* b, double wb,
                                      double* out, long long n, int sm_count, cudaStream_t st);
+size_t gptq_workspace_bytes(long long R);
 cudaError_t launch_gptq_quantize(float* w_work, long long R, long long K, const float* hinv,
                                  const float* scale, const int32_t* zp, int row_stride, int qblock,
-                                 int bits, int symmetric, int8_t* q, cudaStream_t st);
+                                 int bits, int symmetric, int8_t* q, void* ws, cudaStream_t st);
 
 // Unfused element-wise pieces (elementwise.cu).
 cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,

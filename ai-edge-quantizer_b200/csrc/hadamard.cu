@@ -76,6 +76,119 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// ------------------------------------------------------------------ register FWHT
+// The fast path for rows that are a multiple of 256 floats (every FC / embedding width in
+// practice): shared memory is crossed ONCE instead of once per two stages.
+//   phase 1  each warp transforms 256-float groups entirely in registers: lane l holds elements
+//            l + 32 j (j < 8, coalesced 128-byte loads); strides 1..16 are xor-shuffles, strides
+//            32..128 are register butterflies.  Stages at strides >= n are skipped.
+//   phase 2  (n > 256) the remaining strides 256 .. n/2 couple the SAME position of different
+//            groups: a thread takes 4 consecutive positions x G = n / 256 groups from shared
+//            memory (conflict-free LDS.128), finishes the butterflies in registers, scales and
+//            stores 16 bytes per lane straight to global memory.
+__device__ __forceinline__ void warp_fwht256(float (&v)[8], int lane, int n) {
+#pragma unroll
+  for (int h = 1; h < 32; h <<= 1) {
+    if (h < n) {
+      const bool upper = (lane & h) != 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = __shfl_xor_sync(0xffffffffu, v[j], h);
+        v[j] = upper ? o - v[j] : v[j] + o;
+      }
+    }
+  }
+#pragma unroll
+  for (int hj = 1; hj < 8; hj <<= 1) {
+    if (hj * 32 < n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if ((j & hj) == 0) {
+          const float a = v[j], b = v[j | hj];
+          v[j] = a + b;
+          v[j | hj] = a - b;
+        }
+      }
+    }
+  }
+}
+
+template <int G>  // groups of 256 per Hadamard segment (n = 256 * G); G == 1: phase 1 only
+__global__ void __launch_bounds__(256)
+    hadamard_rows_reg(const float* __restrict__ x, long long rows, int cols, int n, float norm,
+                      float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_row[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ngroups = cols >> 8;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* src = x + row * cols;
+    float* dst = out + row * cols;
+    for (int g = warp; g < ngroups; g += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(src + g * 256 + j * 32 + lane);
+      warp_fwht256(v, lane, n);
+      if (G == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[g * 256 + j * 32 + lane] = v[j] * norm;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_row[g * 256 + j * 32 + lane] = v[j];
+      }
+    }
+    if (G > 1) {
+      __syncthreads();
+      // items: (segment, 4-position slot); 64 slots per segment
+      const int nitems = (cols / (256 * G)) * 64;
+      for (int it = tid; it < nitems; it += 256) {
+        const int seg = it >> 6, p4 = (it & 63) * 4;
+        const int base = seg * 256 * G + p4;
+        float4 v[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) v[g] = *reinterpret_cast<const float4*>(&s_row[base + g * 256]);
+#pragma unroll
+        for (int hg = 1; hg < G; hg <<= 1) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if ((g & hg) == 0) {
+              const float4 a = v[g], b = v[g | hg];
+              v[g] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+              v[g | hg] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float4 o = v[g];
+          o.x *= norm; o.y *= norm; o.z *= norm; o.w *= norm;
+          *reinterpret_cast<float4*>(&dst[base + g * 256]) = o;
+        }
+      }
+      __syncthreads();  // s_row is rewritten by the next row
+    }
+  }
+}
+
+template <int G>
+cudaError_t launch_reg(const float* x, long long rows, int cols, int n, float norm, float* out,
+                       int sm_count, cudaStream_t st) {
+  auto kern = hadamard_rows_reg<G>;
+  const int smem = G > 1 ? cols * 4 : 0;
+  static bool configured = false;
+  if (!configured && G > 1) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long per_sm = G > 1 ? 200000 / (smem + 1024) : 8;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sm_count) * per_sm;
+  if (grid > rows) grid = rows;
+  kern<<<static_cast<unsigned>(grid), 256, smem, st>>>(x, rows, cols, n, norm, out);
+  return count_launch();
+}
+
 // Fallback for rows longer than 64 KiB or unaligned / odd shapes: one butterfly
 // stage per launch, in place in global memory (`buf` already holds a copy of x).
 __global__ void __launch_bounds__(256)
@@ -106,6 +219,17 @@ cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols,
   const float norm = 1.0f / sqrtf(static_cast<float>(n));
   const bool smem_ok = cols <= 16384 && cols % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
                        reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (smem_ok && cols % 256 == 0 && n <= 8192) {  // n = 16384 would need 256 data registers
+    const int c = static_cast<int>(cols), nn = static_cast<int>(n);
+    switch (n > 256 ? nn / 256 : 1) {
+      case 1: return launch_reg<1>(x, rows, c, nn, norm, out, sm_count, st);
+      case 2: return launch_reg<2>(x, rows, c, nn, norm, out, sm_count, st);
+      case 4: return launch_reg<4>(x, rows, c, nn, norm, out, sm_count, st);
+      case 8: return launch_reg<8>(x, rows, c, nn, norm, out, sm_count, st);
+      case 16: return launch_reg<16>(x, rows, c, nn, norm, out, sm_count, st);
+      default: return launch_reg<32>(x, rows, c, nn, norm, out, sm_count, st);
+    }
+  }
   if (smem_ok) {
     const int smem = static_cast<int>(cols) * 4;
     static bool configured = false;

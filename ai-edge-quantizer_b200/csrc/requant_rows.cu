@@ -20,6 +20,8 @@
 // and after one named barrier quantises from registers: hoisted exact divide
 // (3 FFMA), magic-number FADD for rint, PRMT byte packing, 128 contiguous bytes
 // written per warp instruction.  HBM is touched once, shared memory once.
+#include <stdlib.h>
+
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
@@ -116,7 +118,7 @@ __device__ __forceinline__ float div_row(float x, const RowQ& rq) {
 
 // ------------------------------------------------------------------ TMA tile stream
 template <int STAGE_BYTES, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
+__global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1)))
     requant_rows_stream(const __grid_constant__ RowsBatch b) {
   static_assert(STAGE_BYTES / (kChunk * 4) == NW * kMaxChunksPerWarp, "chunks per warp");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 8 ? 2 : 1))
     }
     mbar_fence_init();
   }
-  if (tid < 3 * kMaxRowsPerTile) acc_reset(s_acc[tid / kMaxRowsPerTile][tid % kMaxRowsPerTile]);
+  for (int e = tid; e < 3 * kMaxRowsPerTile; e += (NW + 1) * 32)
+    acc_reset(s_acc[e / kMaxRowsPerTile][e % kMaxRowsPerTile]);
   __syncthreads();
 
   if (warp == NW) {  // ---------------- producer
@@ -419,19 +422,30 @@ cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cud
 
 }  // namespace
 
+// Stage size and consumer warps per class.  Smaller stages mean more CTAs per SM, i.e. more
+// independent pass-1 / barrier / pass-2 pipelines to hide each other's bubbles.
+//   1: rows <= 16 KiB, 4 consumer warps, 3 x 16 KiB stages, 4 CTAs / SM
+//   2: rows <= 32 KiB, 8 consumer warps, 3 x 32 KiB stages, 2 CTAs / SM
+//   3: rows <= 64 KiB, 16 consumer warps, 3 x 64 KiB stages, 1 CTA / SM
+static int min_stream_class() {
+  static const int v = getenv("AEQB_ROWS_MIN_CLASS") ? atoi(getenv("AEQB_ROWS_MIN_CLASS")) : 1;
+  return v;
+}
+
 int rows_job_class(const RowsJob& j, int bits) {
   const long long row_bytes = static_cast<long long>(j.cols) * 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
                        (!j.q || reinterpret_cast<uintptr_t>(j.q) % 4 == 0) &&
                        (!j.packed || reinterpret_cast<uintptr_t>(j.packed) % 4 == 0);
   (void)bits;
-  if (aligned && j.cols % kChunk == 0 && row_bytes <= 32768) return 1;
-  if (aligned && j.cols % kChunk == 0 && row_bytes <= 65536) return 2;
-  return 0;
+  if (!aligned || j.cols % kChunk != 0 || row_bytes > 65536) return 0;
+  int k = row_bytes <= 16384 ? 1 : (row_bytes <= 32768 ? 2 : 3);
+  if (k < min_stream_class()) k = min_stream_class();
+  return k;
 }
 
 int rows_job_rows_per_tile(const RowsJob& j, int klass) {
-  const long long stage = klass == 1 ? 32768 : 65536;
+  const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : 65536);
   long long rpt = stage / (static_cast<long long>(j.cols) * 4);
   if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
   return static_cast<int>(rpt);
@@ -440,7 +454,8 @@ int rows_job_rows_per_tile(const RowsJob& j, int klass) {
 cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count,
                                        cudaStream_t st) {
   if (b.n_tiles <= 0) return cudaSuccess;
-  if (klass == 1) return launch_stream<32768, 8>(b, sm_count, 2, st);
+  if (klass == 1) return launch_stream<16384, 4>(b, sm_count, 4, st);
+  if (klass == 2) return launch_stream<32768, 8>(b, sm_count, 2, st);
   return launch_stream<65536, 16>(b, sm_count, 1, st);
 }
 

@@ -221,11 +221,13 @@ AEQB_API int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp,
  *   w_work: [rows, k] fp32 COPY of the weight, updated in place (gptq.py:139 copies too).
  *   scale / zp: scale_cols entries per row: 1 (per channel), k / block (blockwise,
  *   gptq.py:177-189) or 0 (one entry for the whole tensor).  zp may be NULL (zeros).
- *   blocksize: 64 (the reference's only value).  q: [rows, k] int8. */
+ *   blocksize: 64 (the reference's only value).  q: [rows, k] int8.
+ *   ws: aeqb_gptq_workspace_bytes(rows) bytes (the current block's error matrix). */
+AEQB_API size_t aeqb_gptq_workspace_bytes(int64_t rows);
 AEQB_API int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
                                     const float* scale, const int32_t* zp, int64_t scale_cols,
                                     int block, int bits, int symmetric, int blocksize, int8_t* q,
-                                    void* stream);
+                                    void* ws, void* stream);
 
 /* out = (a * wa + b * wb) / (wa + wb), float64: the sample-weighted Hessian mean of
  * qsv_utils._gptq_merge_hessian (utils/qsv_utils.py:71-88).  out may alias a or b. */

@@ -220,3 +220,57 @@ def test_plugin_installs_into_reference_registry():
                                 rq.QuantizeMode.MATERIALIZE)
   assert f.args[0].__module__.startswith("ai_edge_quantizer.")
   assert ram.hadamard_rotation.get_tensor_quant_params is ref_had
+
+
+def test_plugin_prefetch_walks_the_model_like_the_reference(monkeypatch):
+  """plugin.prefetch mirrors params_generator's op walk using the reference's own modules; the
+  arithmetic (GPU) is replaced by a recorder here."""
+  import types
+  from oracle import refshim
+  if not refshim.available():
+    pytest.skip("reference tree not mounted")
+  from aeq_b200 import plugin, prefetch as pf
+  rq = refshim.ref("qtyping")
+  ram = refshim.ref("algorithm_manager")
+  rfu = refshim.ref("utils.tfl_flatbuffer_utils")
+  rcu = refshim.ref("algorithms.utils.common_utils")
+  w = np.zeros((8, 16), np.float32)
+  tensors = [types.SimpleNamespace(name=b"in", shape=[2, 16], buffer=0, type=0, quantization=None),
+             types.SimpleNamespace(name=b"w", shape=[8, 16], buffer=1, type=0, quantization=None),
+             types.SimpleNamespace(name=b"out", shape=[2, 8], buffer=0, type=0, quantization=None)]
+  fc = rq.BuiltinOperator.FULLY_CONNECTED
+  model = types.SimpleNamespace(
+      operatorCodes=[types.SimpleNamespace(builtinCode=fc), types.SimpleNamespace(builtinCode="unknown")],
+      buffers=[types.SimpleNamespace(data=None), types.SimpleNamespace(data=w.tobytes())],
+      subgraphs=[types.SimpleNamespace(tensors=tensors, operators=[
+          types.SimpleNamespace(opcodeIndex=0, inputs=[0, 1, -1], outputs=[2], builtinOptions=None),
+          types.SimpleNamespace(opcodeIndex=1, inputs=[0], outputs=[2], builtinOptions=None)])])
+  cfg = rq.OpQuantizationConfig(weight_tensor_config=rq.TensorQuantizationConfig(num_bits=8))
+
+  class FakeRecipe:
+    def get_quantization_configs(self, op_key, scope):
+      assert op_key == rq.TFLOperationName.FULLY_CONNECTED and scope == "out;"
+      return ram.AlgorithmName.MIN_MAX_UNIFORM_QUANT, cfg
+
+  pgmod = types.ModuleType("fake_params_generator")
+  pgmod.tfl_flatbuffer_utils, pgmod.algorithm_manager, pgmod.qtyping = rfu, ram, rq
+  import sys
+  monkeypatch.setitem(sys.modules, "fake_params_generator", pgmod)
+  PG = type("ParamsGenerator", (), {"__module__": "fake_params_generator"})
+  pg = PG()
+  pg.float_model, pg._tensor_quant_params_cache = model, rcu.TensorQuantParamsCache()
+  seen = {}
+
+  def record(items, cache, make_params=None, get_tensor_data=None):
+    seen["items"], seen["cache"] = list(items), cache
+    seen["params"] = make_params(num_bits=8, quantized_dimension=0, scale=np.ones((8, 1), np.float32),
+                                 zero_point=np.zeros((8, 1), np.int8), symmetric=True)
+    seen["data"] = get_tensor_data(tensors[1], model.buffers)
+    return {"quantized": len(seen["items"])}
+
+  monkeypatch.setattr(pf, "prefetch_weights", record)
+  assert plugin.prefetch(pg, FakeRecipe()) == {"quantized": 1}
+  (info, graph), = seen["items"]
+  assert info.op_name == rq.TFLOperationName.FULLY_CONNECTED and info.subgraph_op_index == 0
+  assert graph.buffers is model.buffers and seen["cache"] is pg._tensor_quant_params_cache
+  assert isinstance(seen["params"], rq.UniformQuantParams) and seen["data"].shape == (8, 16)

@@ -97,6 +97,7 @@ def main():
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     lib.aeqb_hessian_inverse_f64(P(h), C, 0.01, 0, P(hinv), P(hws), P(info), st)
     work = f32(R, C)
+    gws = torch.empty(lib.aeqb_gptq_workspace_bytes(R), dtype=torch.uint8, device=dev)
     sc = (ws_in[0].abs().amax(dim=1) / 7.0).contiguous()
     cases.append(("xtx 8192 tokens (gptq hessian)", lambda i: lib.aeqb_xtx_f32(
         P(x), 8192, C, 0.25, P(h), P(xws) if xws_n else None, st), 0))
@@ -105,7 +106,7 @@ def main():
 
     def gptq_call(i):
       work.copy_(ws_in[0])
-      return lib.aeqb_gptq_quantize_f32(P(work), R, C, P(hinv), P(sc), None, 1, 0, 4, 1, 64, P(q), st)
+      return lib.aeqb_gptq_quantize_f32(P(work), R, C, P(hinv), P(sc), None, 1, 0, 4, 1, 64, P(q), P(gws), st)
     cases.append(("gptq_quantize OBS loop (+copy)", gptq_call, 0))
 
   for name, fn, nbytes in cases:
