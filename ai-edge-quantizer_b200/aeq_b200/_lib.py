@@ -42,6 +42,7 @@ SIGNATURES = {
     "aeqb_minmax_workspace_bytes": (_c.c_size_t, []),
     "aeqb_minmax_tensors_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P]),
     "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),
+    "aeqb_hist_accumulate_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P]),
     "aeqb_row_stats_f32": (_I, [_P, _L, _L, _P, _P, _P, _P]),
     "aeqb_minmax_blocks_f32": (_I, [_P, _L, _L, _I, _P, _P, _P]),
     "aeqb_octav_workspace_bytes": (_c.c_size_t, [_L, _I]),

@@ -436,3 +436,17 @@ def hessian_merge(a: torch.Tensor, wa: float, b: torch.Tensor, wb: float) -> tor
   _lib.call("aeqb_hessian_merge_f64", _ptr(a), float(wa), _ptr(b), float(wb), _ptr(out), a.numel(),
             _stream())
   return out
+
+
+# ------------------------------------------------------------------ histogram
+def hist_accumulate(x: torch.Tensor, lower_bound: float, bin_width: float, nbins: int,
+                    finite_only: bool = True, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """int64 [nbins] bin counts of x (aeqb_hist_accumulate_f32); accumulates into `counts` if given."""
+  if not x.is_cuda or x.dtype != torch.float32:
+    raise ValueError("expected a float32 CUDA tensor")
+  x = x.contiguous()
+  if counts is None:
+    counts = torch.zeros(nbins, dtype=torch.int64, device=x.device)
+  _lib.call("aeqb_hist_accumulate_f32", _ptr(x), x.numel(), float(lower_bound), float(bin_width),
+            int(nbins), int(finite_only), _ptr(counts), _stream())
+  return counts

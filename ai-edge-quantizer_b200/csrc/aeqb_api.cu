@@ -256,6 +256,17 @@ int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int us
   return aeqb_minmax_tensors_f32(&j, 1, lo, hi, use_lo, use_hi, ws, stream);
 }
 
+int aeqb_hist_accumulate_f32(const float* x, int64_t n, float lower_bound, float bin_width, int nbins,
+                             int finite_only, int64_t* counts, void* stream) {
+  if (n < 0) return fail("negative element count");
+  if (nbins < 1 || nbins > 12288) return fail("nbins must be in [1, 12288], got %d", nbins);
+  if (n > 0 && (!x || !counts)) return fail("x / counts are NULL");
+  return check(aeqb::launch_hist(x, n, lower_bound, bin_width, nbins, finite_only,
+                                 reinterpret_cast<long long*>(counts), sm_count(),
+                                 static_cast<cudaStream_t>(stream)),
+               "aeqb_hist_accumulate_f32");
+}
+
 int aeqb_row_stats_f32(const float* x, int64_t rows, int64_t cols, float* mn, float* mx,
                        float* sumsq, void* stream) {
   if (rows < 0 || cols < 0 || cols > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
@@ -402,6 +413,19 @@ int aeqb_quantize_f32(const float* x, int64_t n, int64_t channels, int64_t inner
   if (bits < 2 || bits > 16) return fail("unsupported num_bits %d", bits);
   if (channels <= 0 || inner <= 0) return fail("channels / inner must be positive");
   if (n > 0 && (!x || !scale || !q)) return fail("x / scale / q are NULL");
+  // [channels, inner] matrices with one parameter per row take the tile-stream kernel (one pass,
+  // 128-bit loads, packed stores); every other layout takes the generic element-wise kernel.
+  if ((bits == 2 || bits == 4 || bits == 8) && n == channels * inner && inner <= 0x7fffffff &&
+      (param_stride == 1 || param_stride == 0)) {
+    aeqb::RowsJob j{};
+    j.x = x; j.q = static_cast<int8_t*>(q);
+    j.given_scale = scale; j.given_zp = zp;
+    j.rows = channels; j.cols = static_cast<int>(inner);
+    j.mm_stride = param_stride; j.clip_stride = 0; j.out_stride = 0;
+    if (aeqb::rows_job_class(j, bits) != 0)
+      return run_rows(&j, 1, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
+                      "aeqb_quantize_f32");
+  }
   return check(aeqb::launch_quantize(x, n, channels, inner, scale, zp, param_stride, bits,
                                      symmetric, q, sm_count(), static_cast<cudaStream_t>(stream)),
                "aeqb_quantize_f32");

@@ -30,6 +30,8 @@ struct RowsJob {
   const float* clip;       // optional clipping constants, index row*clip_stride
   const float* given_min;  // optional precomputed min/max (QSV / per-tensor path)
   const float* given_max;
+  const float* given_scale;  // optional final scale (uniform_quantize with caller parameters);
+  const int32_t* given_zp;   //   its zero point, or null for zeros.  Index row * mm_stride.
   long long rows;
   int cols;
   int rows_per_tile;            // launcher
@@ -101,6 +103,8 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
 cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,
                                 cudaStream_t st);
 
+cudaError_t launch_hist(const float* x, long long n, float lb, float bw, int nbins, int finite_only,
+                        long long* counts, int sm_count, cudaStream_t st);
 cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols, float k,
                                   float* scale, int sm_count, cudaStream_t st);
 

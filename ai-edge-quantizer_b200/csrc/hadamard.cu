@@ -119,11 +119,12 @@ __global__ void __launch_bounds__(256)
                       float* __restrict__ out) {
   extern __shared__ __align__(16) float s_row[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
   const int ngroups = cols >> 8;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     const float* src = x + row * cols;
     float* dst = out + row * cols;
-    for (int g = warp; g < ngroups; g += 8) {
+    for (int g = warp; g < ngroups; g += nwarps) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __ldg(src + g * 256 + j * 32 + lane);
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256)
       __syncthreads();
       // items: (segment, 4-position slot); 64 slots per segment
       const int nitems = (cols / (256 * G)) * 64;
-      for (int it = tid; it < nitems; it += 256) {
+      for (int it = tid; it < nitems; it += nthreads) {
         const int seg = it >> 6, p4 = (it & 63) * 4;
         const int base = seg * 256 * G + p4;
         float4 v[G];
@@ -180,12 +181,14 @@ cudaError_t launch_reg(const float* x, long long rows, int cols, int n, float no
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  // Wide segments keep 4 * G floats per thread in phase 2: smaller CTAs keep more rows in flight.
+  const int threads = G >= 8 ? 128 : 256;
   long long per_sm = G > 1 ? 200000 / (smem + 1024) : 8;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 12) per_sm = 12;
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sm_count) * per_sm;
   if (grid > rows) grid = rows;
-  kern<<<static_cast<unsigned>(grid), 256, smem, st>>>(x, rows, cols, n, norm, out);
+  kern<<<static_cast<unsigned>(grid), threads, smem, st>>>(x, rows, cols, n, norm, out);
   return count_launch();
 }
 

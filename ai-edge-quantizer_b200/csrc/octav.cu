@@ -353,7 +353,7 @@ void launch_rows_nv(const float* x, long long rows, int cols, const OctavConst& 
                     float* trace, unsigned* notclose, int sm_count, cudaStream_t st) {
   // Measured on B200 (tools/ktime.py): insensitive to 4..16 CTAs per SM and to the prefetch; the
   // kernel is issue-bound (IPC 2.45 of 4), see profiles/.
-  const int per_sm = (2048 / T) < 8 ? (2048 / T) : 8;
+  const int per_sm = (2048 / T) < 12 ? (2048 / T) : 12;
   long long grid = static_cast<long long>(sm_count) * per_sm;
   if (grid > rows) grid = rows;
   octav_rows_trace<NV, T, false><<<static_cast<unsigned>(grid), T, 0, st>>>(x, rows, cols, k, iters,
@@ -385,7 +385,7 @@ cudaError_t launch_octav_rows(const float* x, long long rows, long long cols, in
     if (v4 <= 128) launch_rows_nv<1, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else if (v4 <= 256) launch_rows_nv<2, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else if (v4 <= 512) launch_rows_nv<4, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
-    else if (v4 <= 1024) launch_rows_nv<8, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 1024) launch_rows_nv<16, 64>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else if (v4 <= 2048) launch_rows_nv<8, 256>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else launch_rows_nv<8, 512>(x, rows, c, k, iters, trace, notclose, sm_count, st);
   } else {

@@ -8,6 +8,8 @@
 // All use 128-bit ld.global.nc loads, warp-shuffle reductions with NaN
 // propagation (np.min / np.max semantics) and ordered-int atomics for the
 // cross-CTA merge, so results are order-free and bit-exact.
+#include <limits.h>
+
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
@@ -265,6 +267,44 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ---------------------------------------------------------------- histogram
+// The bin-count step of histogram_utils._DynamicHistogram1D.add (utils/histogram_utils.py:139-164):
+//   idx = clip(int32(floor((x - lower_bound) / bin_width)), 0, nbins - 1);  counts[idx] += 1
+// in fp32 like NumPy does for an fp32 array with fp32 / weak scalars.  Out-of-int32-range
+// quotients and NaN cast to INT_MIN on x86 (cvttss2si) and therefore clip to bin 0; mirrored.
+// finite_only drops NaN / +-inf first (DynamicHistogram.add filters with np.isfinite, :401-416).
+// Shared-memory privatised counters (one copy per CTA), merged with 64-bit global atomics.
+__global__ void __launch_bounds__(256)
+    hist_kernel(const float* __restrict__ x, long long n, float lb, float bw, int nbins,
+                int finite_only, unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned s_bins[];
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_bins[i] = 0;
+  __syncthreads();
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  auto add1 = [&](float v) {
+    if (finite_only && !(fabsf(v) < INFINITY)) return;
+    const float t = floorf(__fdiv_rn(__fsub_rn(v, lb), bw));
+    int idx = (t >= -2147483648.0f && t < 2147483648.0f) ? static_cast<int>(t) : INT_MIN;
+    idx = min(max(idx, 0), nbins - 1);
+    atomicAdd(&s_bins[idx], 1u);
+  };
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+  long long head = ((16 - (addr & 15)) & 15) / 4;
+  if (head > n) head = n;
+  const long long nvec = (n - head) / 4;
+  const float4* xv = reinterpret_cast<const float4*>(x + head);
+  for (long long i = tid; i < head; i += nthreads) add1(x[i]);
+  for (long long i = tid; i < nvec; i += nthreads) {
+    const float4 v = ldg_stream(xv + i);
+    add1(v.x); add1(v.y); add1(v.z); add1(v.w);
+  }
+  for (long long j = head + nvec * 4 + tid; j < n; j += nthreads) add1(x[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+    if (s_bins[i]) atomicAdd(&counts[i], static_cast<unsigned long long>(s_bins[i]));
+}
+
 // ---------------------------------------------------------------- per block
 // block/8 lanes share a block; each lane owns 8 consecutive floats.
 template <int BLOCK>
@@ -351,6 +391,18 @@ cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols
   long long grid = static_cast<long long>(sm_count) * (threads == 1024 ? 2 : 8);
   if (grid > rows) grid = rows;
   mse_scale_rows_kernel<<<static_cast<unsigned>(grid), threads, 0, st>>>(x, rows, cols, k, scale);
+  return count_launch();
+}
+
+cudaError_t launch_hist(const float* x, long long n, float lb, float bw, int nbins, int finite_only,
+                        long long* counts, int sm_count, cudaStream_t st) {
+  if (n <= 0 || nbins <= 0) return cudaSuccess;
+  if (nbins > 12288) return cudaErrorInvalidValue;  // 48 KiB of shared counters
+  long long grid = (n / 4 + 255) / 256;
+  if (grid > sm_count * 8LL) grid = sm_count * 8LL;
+  if (grid < 1) grid = 1;
+  hist_kernel<<<static_cast<unsigned>(grid), 256, nbins * sizeof(unsigned), st>>>(
+      x, n, lb, bw, nbins, finite_only, reinterpret_cast<unsigned long long*>(counts));
   return count_launch();
 }
 

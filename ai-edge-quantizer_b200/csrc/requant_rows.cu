@@ -70,6 +70,15 @@ __device__ __forceinline__ RowQ finalize_row(const RowsJob& a, int bits, bool sy
                                             float mn, float mx, float xmax, bool publish) {
   const QRange qr = qrange(bits, sym);
   float scale, zpf = 0.0f;
+  if (a.given_scale) {  // uniform_quantize (uqt:273-362) with the caller's parameters, no statistics
+    RowQ g;
+    g.b = a.given_scale[row * a.mm_stride];
+    g.zp = a.given_zp ? static_cast<float>(a.given_zp[row * a.mm_stride]) : 0.0f;
+    const DivBy d = make_div(g.b, xmax);
+    g.y = d.y;
+    g.mode = d.fast ? kFastClamp : kSlow;
+    return g;
+  }
   if (sym) {
     float bound = max_nan(max_nan(fabsf(mn), fabsf(mx)), 1e-9f);
     if (a.clip) {
@@ -106,8 +115,9 @@ __device__ __forceinline__ RowQ finalize_row(const RowsJob& a, int bits, bool sy
 }
 
 __device__ __forceinline__ int quant_slow(float x, const RowQ& rq, bool sym, int lo, int hi) {
-  float t = __fdiv_rn(x, rq.b);
-  if (!sym) t = __fadd_rn(t, rq.zp);
+  (void)sym;
+  // x / scale + zp; adding a zero zero-point only turns -0 into +0, which rounds the same.
+  const float t = __fadd_rn(__fdiv_rn(x, rq.b), rq.zp);
   return clampi(rni(t), lo, hi);
 }
 
@@ -188,13 +198,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     const int cols = job.cols;
     const int cpr = cols / kChunk;
     const int nchunks = nrows * cpr;
-    const bool given = job.given_min != nullptr;
+    // Caller-supplied min / max: no scan.  Caller-supplied scale: |x| max is still scanned (free
+    // at HBM speed) because it decides whether the hoisted divide may be used.
+    const bool gscale = job.given_scale != nullptr;
+    const bool given = job.given_min != nullptr && !gscale;
+    const bool abs_scan = gscale || sym;
 
     // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
     // atomic per chunk merges the row statistics (no row-change bookkeeping).
     const unsigned magic = job.cpr_magic;  // row of chunk c = (c * magic) >> 20
     const bool full_tile = nchunks == NW * kMaxChunksPerWarp;
-    const bool plain = sym && !given;
+    const bool plain = abs_scan && !given;
     float4 v[kMaxChunksPerWarp];
     if (plain && full_tile) {  // branch-free common case
 #pragma unroll
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         v[j] = t4[c * 32 + lane];
         if (!given) {
           const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
-          if (sym) {
+          if (abs_scan) {
             const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
             if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
           } else {
@@ -255,7 +269,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
       float mn, mx, xmax;
-      if (given) {
+      if (gscale) {
+        mx = __uint_as_float(s_acc[buf][r].amax_bits);  // finalize_row only uses xmax here
+        mn = -mx;
+        xmax = mx;
+      } else if (given) {
         mn = jcopy.given_min[grow * jcopy.mm_stride];
         mx = jcopy.given_max[grow * jcopy.mm_stride];
         xmax = INFINITY;  // row not scanned: always take the IEEE divide
@@ -326,10 +344,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
             if (rq.mode != kSlow) {
               float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq), t2 = div_row(v[j].z, rq),
                     t3 = div_row(v[j].w, rq);
-              if (!sym) {
-                t0 = __fadd_rn(t0, rq.zp); t1 = __fadd_rn(t1, rq.zp);
-                t2 = __fadd_rn(t2, rq.zp); t3 = __fadd_rn(t3, rq.zp);
-              }
+              // + zero point (0 when symmetric: only turns -0 into +0, which rounds the same)
+              t0 = __fadd_rn(t0, rq.zp); t1 = __fadd_rn(t1, rq.zp);
+              t2 = __fadd_rn(t2, rq.zp); t3 = __fadd_rn(t3, rq.zp);
               q0 = clampi(rni(t0), qr.lo, qr.hi); q1 = clampi(rni(t1), qr.lo, qr.hi);
               q2 = clampi(rni(t2), qr.lo, qr.hi); q3 = clampi(rni(t3), qr.lo, qr.hi);
             } else {
@@ -374,7 +391,10 @@ __global__ void __launch_bounds__(256)
   const QRange qr = qrange(bits, sym);
   const float* x = a.x + row * a.cols;
   float mn, mx, xmax;
-  if (a.given_min) {
+  if (a.given_scale) {
+    mn = mx = 0.0f;
+    xmax = INFINITY;
+  } else if (a.given_min) {
     mn = a.given_min[row * a.mm_stride];
     mx = a.given_max[row * a.mm_stride];
     xmax = INFINITY;

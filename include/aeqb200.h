@@ -154,6 +154,14 @@ AEQB_API int aeqb_minmax_tensors_f32(const aeqb_minmax_job* jobs, int64_t n_jobs
 AEQB_API int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int use_lo,
                                     int use_hi, float* out2, void* ws, void* stream);
 
+/* counts[clip(int32(floor((x - lower_bound) / bin_width)), 0, nbins - 1)] += 1 for every element
+ * (finite ones only when finite_only != 0): the bin-count step of
+ * histogram_utils._DynamicHistogram1D.add (utils/histogram_utils.py:139-164) and the np.isfinite
+ * filter of DynamicHistogram.add (:396-416).  counts: DEVICE int64 [nbins], accumulated into
+ * (zero it for a fresh batch).  nbins <= 12288. */
+AEQB_API int aeqb_hist_accumulate_f32(const float* x, int64_t n, float lower_bound, float bin_width,
+                                      int nbins, int finite_only, int64_t* counts, void* stream);
+
 /* Per-row min, max and sum of squares of a [rows, cols] matrix (any may be
  * NULL).  min/max: common_quantize.init_tensor_min_max CHANNELWISE branch
  * (common_quantize.py:1337-1344); sumsq: the reduction of mse.get_tensor_quant_params

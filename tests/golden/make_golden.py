@@ -61,7 +61,8 @@ def main():
   only = set(sys.argv[1:])
   for name, fn in (("minmax", gen_minmax), ("octav", gen_octav), ("mse", gen_mse),
                    ("hadamard", gen_hadamard), ("gptq", gen_gptq),
-                   ("calibration", gen_calibration), ("pack", gen_pack)):
+                   ("calibration", gen_calibration), ("pack", gen_pack),
+                   ("histogram", gen_histogram)):
     if not only or name in only:
       fn()
 
@@ -209,6 +210,47 @@ def gen_pack():
     out[f"b{bits}_n{n}_in"] = v
     out[f"b{bits}_n{n}_out"] = TU.pack_data(bits, v.view(np.uint8).copy())
   save("pack", **out)
+
+
+def gen_histogram():
+  # ---- DynamicHistogram (utils/histogram_utils.py): per-tensor growth / compaction, per-channel,
+  # initial_bin_width, non-finite filtering and a resampled merge
+  HU = refshim.ref("utils.histogram_utils")
+  out = {}
+  rng = np.random.default_rng(77)
+  batches = [rng.standard_normal((4, 33, 65)).astype(np.float32) * s for s in (1.0, 0.5, 3.0, 40.0, 2.0)]
+  batches[1][0, 0, 0] = np.inf
+  batches[2][1, 2, 3] = np.nan
+  batches[2][1, 2, 4] = -np.inf
+  for j, b in enumerate(batches):
+    out[f"b{j}"] = b
+
+  def dump(prefix, h):
+    for c, impl in enumerate(h._impls):
+      out[f"{prefix}_c{c}_counts"] = np.array(impl.counts, copy=True)  # add() updates in place
+      out[f"{prefix}_c{c}_lb"] = np.array(impl.lower_bound)
+      out[f"{prefix}_c{c}_bw"] = np.array(impl.bin_width)
+      out[f"{prefix}_c{c}_min"] = np.array(impl.global_min)
+      out[f"{prefix}_c{c}_max"] = np.array(impl.global_max)
+
+  h = HU.DynamicHistogram(max_tensor_bins=2048)
+  for j, b in enumerate(batches):
+    h.add(b)
+    dump(f"t_after{j}", h)
+  h2 = HU.DynamicHistogram(max_tensor_bins=256, initial_bin_width=0.05)
+  for b in batches[:3]:
+    h2.add(b)
+  dump("w", h2)
+  hc = HU.DynamicHistogram(max_tensor_bins=2048, axis=0)
+  for b in batches[:4]:
+    hc.add(b)
+  dump("ch", hc)
+  a, bb = HU.DynamicHistogram(max_tensor_bins=512), HU.DynamicHistogram(max_tensor_bins=512)
+  a.add(batches[0]); a.add(batches[2])
+  bb.add(batches[3])
+  a.merge(bb)
+  dump("merged", a)
+  save("histogram", **out)
 
 
 if __name__ == "__main__":

@@ -43,8 +43,9 @@ def main():
   f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
   q = torch.empty(n, dtype=torch.int8, device=dev)
   pk = torch.empty(n // 2, dtype=torch.uint8, device=dev)
-  scale, zp = f32(R), torch.empty(R, dtype=torch.int32, device=dev)
-  clip_r, clip_b = f32(R), f32(n // 32)
+  # valid parameters (not torch.empty garbage: degenerate scales take the IEEE-divide path)
+  scale, zp = torch.full((R,), 1e-3, device=dev), torch.zeros(R, dtype=torch.int32, device=dev)
+  clip_r, clip_b = torch.full((R,), 0.05, device=dev), torch.full((n // 32,), 0.05, device=dev)
   bscale = torch.empty(n // 32, dtype=torch.float16, device=dev)
   out2 = f32(NT, 2)
   rot = f32(R, C)
