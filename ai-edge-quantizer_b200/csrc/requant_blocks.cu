@@ -160,17 +160,22 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
       uint32_t word_q0 = 0, word_q1 = 0, word_p = 0;
       if (fast) {
         const DivBy d = make_recip(scale);
-        const float t0 = div_fast(va.x, d), t1 = div_fast(va.y, d), t2 = div_fast(va.z, d),
-                    t3 = div_fast(va.w, d), t4_ = div_fast(vb.x, d), t5 = div_fast(vb.y, d),
-                    t6 = div_fast(vb.z, d), t7 = div_fast(vb.w, d);
+        const float2 t01 = div_fast2(make_float2(va.x, va.y), d.b, d.y);
+        const float2 t23 = div_fast2(make_float2(va.z, va.w), d.b, d.y);
+        const float2 t45 = div_fast2(make_float2(vb.x, vb.y), d.b, d.y);
+        const float2 t67 = div_fast2(make_float2(vb.z, vb.w), d.b, d.y);
         if (OUT_P) {
-          const uint32_t ha = nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3));
-          const uint32_t hb = nibbles4_biased(rmagic8(t4_), rmagic8(t5), rmagic8(t6), rmagic8(t7));
+          const uint2 r01 = rmagic2(t01, kMagicPlus8), r23 = rmagic2(t23, kMagicPlus8);
+          const uint2 r45 = rmagic2(t45, kMagicPlus8), r67 = rmagic2(t67, kMagicPlus8);
+          const uint32_t ha = nibbles4_biased(r01.x, r01.y, r23.x, r23.y);
+          const uint32_t hb = nibbles4_biased(r45.x, r45.y, r67.x, r67.y);
           word_p = __byte_perm(ha, hb, sel) ^ 0x88888888u;
         }
         if (OUT_Q) {
-          word_q0 = bytes4(rmagic(t0), rmagic(t1), rmagic(t2), rmagic(t3));
-          word_q1 = bytes4(rmagic(t4_), rmagic(t5), rmagic(t6), rmagic(t7));
+          const uint2 r01 = rmagic2(t01, kMagic), r23 = rmagic2(t23, kMagic);
+          const uint2 r45 = rmagic2(t45, kMagic), r67 = rmagic2(t67, kMagic);
+          word_q0 = bytes4(r01.x, r01.y, r23.x, r23.y);
+          word_q1 = bytes4(r45.x, r45.y, r67.x, r67.y);
         }
       } else {
         scale = block_scale_slow(amax, clip, blk0 + blk, b.bits, qr.qmax, &h16);

@@ -211,6 +211,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     const bool plain = abs_scan && !given;
     float4 v[kMaxChunksPerWarp];
     if (plain && full_tile) {  // branch-free common case
+      // (Folding the 8 per-chunk atomics into one divergent region per tile, or sleeping between
+      //  mbarrier polls, both measured SLOWER on B200: 0.85 / 0.91 vs 0.92 of peak.)
 #pragma unroll
       for (int j = 0; j < kMaxChunksPerWarp; ++j) {
         const int c = warp + j * NW;
@@ -305,11 +307,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
 #pragma unroll
       for (int j = 0; j < kMaxChunksPerWarp; ++j) {
         const float2 by = s_by[warp][j];
-        RowQ rq;
-        rq.b = by.x; rq.y = by.y;
-        const float t0 = div_row(v[j].x, rq), t1 = div_row(v[j].y, rq),
-                    t2 = div_row(v[j].z, rq), t3 = div_row(v[j].w, rq);
-        if (ql) *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) = bytes4(rmagic(t0), rmagic(t1), rmagic(t2), rmagic(t3));
+        // The hoisted exact divide on the packed-fp32 pipe: two elements per FMUL2 / FFMA2
+        // (same three roundings per element as the scalar sequence, so still bit-identical).
+        const float2 yy = make_float2(by.y, by.y), nb = make_float2(-by.x, -by.x);
+        const float2 xa = make_float2(v[j].x, v[j].y), xb = make_float2(v[j].z, v[j].w);
+        const float2 qa0 = __fmul2_rn(xa, yy), qb0 = __fmul2_rn(xb, yy);
+        const float2 qa = __ffma2_rn(yy, __ffma2_rn(nb, qa0, xa), qa0);
+        const float2 qb = __ffma2_rn(yy, __ffma2_rn(nb, qb0, xb), qb0);
+        const float t0 = qa.x, t1 = qa.y, t2 = qb.x, t3 = qb.y;
+        if (ql) {
+          const float2 mg = make_float2(kMagic, kMagic);
+          const float2 ra = __fadd2_rn(qa, mg), rb = __fadd2_rn(qb, mg);
+          *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) =
+              bytes4(__float_as_uint(ra.x), __float_as_uint(ra.y), __float_as_uint(rb.x), __float_as_uint(rb.y));
+        }
         if (pl) {
           const uint32_t h =
               (nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3)) ^ 0x8888u) & 0xFFFFu;
