@@ -126,6 +126,33 @@ __device__ __forceinline__ float div_row(float x, const RowQ& rq) {
   return fmaf(rq.y, fmaf(-rq.b, q0, x), q0);
 }
 
+// Pass 2 of a tile whose rows are all symmetric / unclipped / inside the divide window.  FULL
+// tiles are branch-free; partial ones (row length not a multiple of NW chunks, tensor tails) stop
+// at the first unused chunk slot (warp-uniform: slots fill in order).
+template <bool FULL, int NW>
+__device__ __forceinline__ void tight_pass2(const float4 (&v)[kMaxChunksPerWarp], const float2* by_slots,
+                                            int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks) {
+#pragma unroll
+  for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+    if (!FULL && warp + j * NW >= nchunks) break;
+    const float2 by = by_slots[j];
+    // The hoisted exact divide on the packed-fp32 pipe: two elements per FMUL2 / FFMA2
+    // (same three roundings per element as the scalar sequence, so still bit-identical).
+    const float2 qa = div_fast2(make_float2(v[j].x, v[j].y), by.x, by.y);
+    const float2 qb = div_fast2(make_float2(v[j].z, v[j].w), by.x, by.y);
+    if (ql) {
+      const uint2 ra = rmagic2(qa, kMagic), rb = rmagic2(qb, kMagic);
+      *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) = bytes4(ra.x, ra.y, rb.x, rb.y);
+    }
+    if (pl) {
+      const uint2 ra = rmagic2(qa, kMagicPlus8), rb = rmagic2(qb, kMagicPlus8);
+      const uint32_t h = (nibbles4_biased(ra.x, ra.y, rb.x, rb.y) ^ 0x8888u) & 0xFFFFu;
+      const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
+      if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(pl + j * NW * (kChunk / 2)) = h | (o << 16);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA tile stream
 template <int STAGE_BYTES, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1)))
@@ -211,8 +238,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     const bool plain = abs_scan && !given;
     float4 v[kMaxChunksPerWarp];
     if (plain && full_tile) {  // branch-free common case
-      // (Folding the 8 per-chunk atomics into one divergent region per tile, or sleeping between
-      //  mbarrier polls, both measured SLOWER on B200: 0.85 / 0.91 vs 0.92 of peak.)
+      // (Measured SLOWER on B200, 0.85-0.91 vs 0.92 of peak: folding the per-chunk atomics into
+      //  one divergent region per tile; folding the chunks of a row in registers before one
+      //  REDUX + atomic per row; sleeping between mbarrier polls.  The pass-1 -> barrier -> pass-2
+      //  critical path wants short independent chains, not fewer instructions.)
 #pragma unroll
       for (int j = 0; j < kMaxChunksPerWarp; ++j) {
         const int c = warp + j * NW;
@@ -220,6 +249,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
         const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
         if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
+      }
+    } else if (plain) {  // partial tile (row length not a multiple of NW chunks, tensor tail)
+#pragma unroll
+      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+        const int c = warp + j * NW;
+        if (c < nchunks) {  // warp-uniform
+          v[j] = t4[c * 32 + lane];
+          const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
+          const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
+          if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
+        }
       }
     } else
 #pragma unroll
@@ -266,7 +306,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     // ---- per-row scale / zero point, one lane per chunk slot (no second barrier):
     // the row's first chunk owner publishes scale / zp to global memory.
     RowQ mine;
-    mine.b = 1.0f; mine.y = 1.0f; mine.zp = 0.0f; mine.mode = kSlow;
+    mine.b = 1.0f; mine.y = 1.0f; mine.zp = 0.0f; mine.mode = kFastSym;  // unused slots must not veto the tight path
     if (my_valid) {
       const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
@@ -297,37 +337,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
 
     // ---- pass 2: quantise from registers + store
     const bool all_fast = __all_sync(0xffffffffu, lane >= kMaxChunksPerWarp || mine.mode == kFastSym);
-    if (full_tile && all_fast && !(pp && bits != 4)) {
+    if (all_fast && !(pp && bits != 4)) {
       // Tight path: every row of the tile is symmetric / unclipped / in the divide
       // window.  (scale, reciprocal) per chunk slot via one broadcast LDS.64.
       if (lane < kMaxChunksPerWarp) s_by[warp][lane] = make_float2(mine.b, mine.y);
       __syncwarp();
       int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
       uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
-#pragma unroll
-      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
-        const float2 by = s_by[warp][j];
-        // The hoisted exact divide on the packed-fp32 pipe: two elements per FMUL2 / FFMA2
-        // (same three roundings per element as the scalar sequence, so still bit-identical).
-        const float2 yy = make_float2(by.y, by.y), nb = make_float2(-by.x, -by.x);
-        const float2 xa = make_float2(v[j].x, v[j].y), xb = make_float2(v[j].z, v[j].w);
-        const float2 qa0 = __fmul2_rn(xa, yy), qb0 = __fmul2_rn(xb, yy);
-        const float2 qa = __ffma2_rn(yy, __ffma2_rn(nb, qa0, xa), qa0);
-        const float2 qb = __ffma2_rn(yy, __ffma2_rn(nb, qb0, xb), qb0);
-        const float t0 = qa.x, t1 = qa.y, t2 = qb.x, t3 = qb.y;
-        if (ql) {
-          const float2 mg = make_float2(kMagic, kMagic);
-          const float2 ra = __fadd2_rn(qa, mg), rb = __fadd2_rn(qb, mg);
-          *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) =
-              bytes4(__float_as_uint(ra.x), __float_as_uint(ra.y), __float_as_uint(rb.x), __float_as_uint(rb.y));
-        }
-        if (pl) {
-          const uint32_t h =
-              (nibbles4_biased(rmagic8(t0), rmagic8(t1), rmagic8(t2), rmagic8(t3)) ^ 0x8888u) & 0xFFFFu;
-          const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1);
-          if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(pl + j * NW * (kChunk / 2)) = h | (o << 16);
-        }
-      }
+      if (full_tile) tight_pass2<true, NW>(v, s_by[warp], ql, pl, lane, warp, nchunks);
+      else tight_pass2<false, NW>(v, s_by[warp], ql, pl, lane, warp, nchunks);
       __syncwarp();  // s_by[warp] is rewritten next tile
     } else {
 #pragma unroll
