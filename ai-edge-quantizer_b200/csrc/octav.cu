@@ -30,6 +30,7 @@ namespace aeqb {
 namespace {
 
 constexpr int kMaxIter = 32;
+constexpr int kTensorMaxParts = 1024;
 
 struct OctavConst {
   float s;         // f32(4^-bits / divisor)
@@ -320,6 +321,95 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0 && s_mask) atomicOr(notclose, s_mask);
 }
 
+// ------------------------------------------------------------------ whole tensor (TENSORWISE)
+// One reduction group = the whole tensor: iteration i needs a grid-wide masked sum, so each
+// iteration is two launches over the (L2-resident for <= ~100 MB) tensor: per-CTA partials, then a
+// one-CTA step that folds them in fixed order, applies the update and appends to the trace.
+// state: [0] current guess (float), [1] zeros count (as int bits), [2..] unused.
+struct TensorPartial {
+  double sum;
+  long long cnt;
+  long long zeros;
+};
+
+__global__ void __launch_bounds__(256)
+    octav_tensor_partials(const float* __restrict__ x, long long n, const float* __restrict__ state,
+                          TensorPartial* __restrict__ part) {
+  __shared__ double s_sum[8];
+  __shared__ long long s_cnt[8], s_zero[8];
+  const float g = state[0];
+  const bool live = g == g;  // a NaN guess selects nothing
+  float2 sum = make_float2(0.f, 0.f), cnt = make_float2(0.f, 0.f);
+  double dsum = 0.0;
+  long long dcnt = 0, zeros = 0;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+  long long head = ((16 - (addr & 15)) & 15) / 4;
+  if (head > n) head = n;
+  const long long nvec = (n - head) / 4;
+  const float4* xv = reinterpret_cast<const float4*>(x + head);
+  int run = 0;
+  for (long long i = tid; i < nvec; i += nthreads) {
+    const float4 v = __ldg(xv + i);
+    int z = 0;
+    const float a0 = condition(v.x, z), a1 = condition(v.y, z), a2 = condition(v.z, z), a3 = condition(v.w, z);
+    zeros += z;
+    if (live) {
+      acc_pair(a0, a1, g, sum, cnt);
+      acc_pair(a2, a3, g, sum, cnt);
+    }
+    if (++run == 64) {  // bound the fp32 partial runs, keep the long accumulation in fp64
+      dsum += static_cast<double>(sum.x) + static_cast<double>(sum.y);
+      dcnt += static_cast<long long>(cnt.x + cnt.y);
+      sum = make_float2(0.f, 0.f); cnt = make_float2(0.f, 0.f);
+      run = 0;
+    }
+  }
+  // scalar head / tail
+  for (long long i = tid; i < head + (n - head - nvec * 4); i += nthreads) {
+    const long long e = i < head ? i : nvec * 4 + i;
+    int z = 0;
+    const float a = condition(x[e], z);
+    zeros += z;
+    if (live && a >= g) { dsum += static_cast<double>(a); dcnt += 1; }
+  }
+  dsum += static_cast<double>(sum.x) + static_cast<double>(sum.y);
+  dcnt += static_cast<long long>(cnt.x + cnt.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_sum[warp] = dsum; s_cnt[warp] = dcnt; s_zero[warp] = zeros; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    TensorPartial t{0.0, 0, 0};
+    for (int w = 0; w < 8; ++w) { t.sum += s_sum[w]; t.cnt += s_cnt[w]; t.zeros += s_zero[w]; }
+    part[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+    octav_tensor_step(const TensorPartial* __restrict__ part, int nparts, OctavConst k, int it,
+                      float* __restrict__ state, float* __restrict__ trace,
+                      unsigned* __restrict__ notclose) {
+  if (threadIdx.x != 0) return;
+  double sum = 0.0;
+  long long cnt = 0, zeros = 0;
+  for (int i = 0; i < nparts; ++i) { sum += part[i].sum; cnt += part[i].cnt; zeros += part[i].zeros; }
+  const float g = state[0];
+  if (g == 0.0f) cnt += zeros;
+  const float ng = octav_update_ll(static_cast<float>(sum), cnt, k);
+  trace[it] = ng;
+  if (!is_close(g, ng)) atomicOr(notclose, 1u << it);
+  state[0] = ng;
+}
+
+__global__ void octav_tensor_init(float* state) { state[0] = 1.0f; }
+
 // clip[g] = trace[stop][g], stop = first iteration after which every group was
 // converged (octav.py:109), else the last iteration.
 __global__ void __launch_bounds__(256)
@@ -363,7 +453,9 @@ void launch_rows_nv(const float* x, long long rows, int cols, const OctavConst& 
 }  // namespace
 
 size_t octav_workspace_bytes(long long groups, int iters) {
-  return static_cast<size_t>(groups) * static_cast<size_t>(iters) * sizeof(float) + 256;
+  // mask slot + trace [+ per-CTA partials of the whole-tensor path, used when groups == 1]
+  return static_cast<size_t>(groups) * static_cast<size_t>(iters) * sizeof(float) + 1024 +
+         static_cast<size_t>(kTensorMaxParts) * sizeof(TensorPartial);
 }
 
 // ws layout: [0, 256) the not-close mask (4 bytes used), then the trace.
@@ -377,6 +469,20 @@ cudaError_t launch_octav_rows(const float* x, long long rows, long long cols, in
   cudaError_t e = cudaMemsetAsync(notclose, 0, 256, st);
   if (e != cudaSuccess) return e;
   const OctavConst k = make_const(bits, divisor, cols);
+  if (rows == 1 && cols > 65536) {  // whole-tensor group: grid-wide reduction per iteration
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    float* state = reinterpret_cast<float*>(base + 64);
+    TensorPartial* part = reinterpret_cast<TensorPartial*>(base + 1024);  // past mask, state and the <= 128 B trace
+    int grid = sm_count * 4;
+    if (grid > kTensorMaxParts) grid = kTensorMaxParts;
+    octav_tensor_init<<<1, 1, 0, st>>>(state);
+    for (int it = 0; it < iters; ++it) {
+      octav_tensor_partials<<<grid, 256, 0, st>>>(x, cols, state, part);
+      octav_tensor_step<<<1, 32, 0, st>>>(part, grid, k, it, state, trace, notclose);
+    }
+    octav_select<<<1, 256, 0, st>>>(trace, notclose, 1, iters, early_stop, clip);
+    return count_launch(2 + 2 * iters);
+  }
   const bool vec = cols > 0 && cols % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
                    cols <= 16384;
   if (vec) {
