@@ -48,7 +48,8 @@ SIGNATURES = {
     "aeqb_octav_workspace_bytes": (_c.c_size_t, [_L, _I]),
     "aeqb_octav_clip_rows_f32": (_I, [_P, _L, _L, _I, _I, _F, _I, _P, _P, _P]),
     "aeqb_octav_clip_blocks_f32": (_I, [_P, _L, _L, _I, _I, _I, _F, _I, _P, _P, _P]),
-    "aeqb_mse_scale_rows_f32": (_I, [_P, _L, _L, _F, _P, _P]),
+    "aeqb_mse_workspace_bytes": (_c.c_size_t, []),
+    "aeqb_mse_scale_rows_f32": (_I, [_P, _L, _L, _F, _P, _P, _P]),
     "aeqb_hadamard_rows_f32": (_I, [_P, _L, _L, _L, _P, _P]),
     "aeqb_xtx_workspace_bytes": (_c.c_size_t, [_L, _L]),
     "aeqb_xtx_f32": (_I, [_P, _L, _L, _D, _P, _P, _P]),

@@ -344,8 +344,9 @@ def mse_scale_rows(x: torch.Tensor, multiplier: float) -> torch.Tensor:
   _check_f32_2d(x)
   rows, cols = x.shape
   scale = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+  ws = torch.empty(_lib.load().aeqb_mse_workspace_bytes(), dtype=torch.uint8, device=x.device)
   _lib.call("aeqb_mse_scale_rows_f32", _ptr(x), rows, cols, float(multiplier), _ptr(scale),
-            _stream())
+            _ptr(ws), _stream())
   return scale
 
 

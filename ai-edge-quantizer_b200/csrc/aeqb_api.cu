@@ -320,11 +320,13 @@ int aeqb_octav_clip_blocks_f32(const float* x, int64_t rows, int64_t cols, int b
                "aeqb_octav_clip_blocks_f32");
 }
 
+size_t aeqb_mse_workspace_bytes(void) { return aeqb::mse_workspace_bytes(); }
+
 int aeqb_mse_scale_rows_f32(const float* x, int64_t rows, int64_t cols, float k, float* scale,
-                            void* stream) {
+                            void* ws, void* stream) {
   if (rows < 0 || cols <= 0) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
   if (rows > 0 && (!x || !scale)) return fail("x / scale are NULL");
-  return check(aeqb::launch_mse_scale_rows(x, rows, cols, k, scale, sm_count(),
+  return check(aeqb::launch_mse_scale_rows(x, rows, cols, k, scale, ws, sm_count(),
                                            static_cast<cudaStream_t>(stream)),
                "aeqb_mse_scale_rows_f32");
 }

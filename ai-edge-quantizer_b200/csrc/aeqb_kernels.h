@@ -105,8 +105,9 @@ cudaError_t launch_block_minmax(const float* x, long long n, int block, float* m
 
 cudaError_t launch_hist(const float* x, long long n, float lb, float bw, int nbins, int finite_only,
                         long long* counts, int sm_count, cudaStream_t st);
+size_t mse_workspace_bytes();
 cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols, float k,
-                                  float* scale, int sm_count, cudaStream_t st);
+                                  float* scale, void* ws, int sm_count, cudaStream_t st);
 
 // OCTAV clipping search (octav.cu).  ws: octav_workspace_bytes(groups, iters) bytes.
 size_t octav_workspace_bytes(long long groups, int iters);

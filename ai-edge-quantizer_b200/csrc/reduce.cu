@@ -267,6 +267,37 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// Whole tensor (rows == 1, TENSORWISE): per-CTA fp64 partial sums of fp32 squares, folded in fixed
+// order by one thread (deterministic), then the same fp32 divide / sqrt / multiply.
+constexpr int kMseMaxParts = 1024;
+__global__ void __launch_bounds__(256)
+    mse_tensor_partials(const float* __restrict__ x, long long n, double* __restrict__ part) {
+  __shared__ double s_part[8];
+  double acc = 0.0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    acc += static_cast<double>(__fmul_rn(v, v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    part[blockIdx.x] = t;
+  }
+}
+
+__global__ void mse_tensor_final(const double* __restrict__ part, int nparts, long long n, float k,
+                                 float* __restrict__ scale) {
+  double t = 0.0;
+  for (int i = 0; i < nparts; ++i) t += part[i];
+  const float mean = __fdiv_rn(static_cast<float>(t), static_cast<float>(n));
+  scale[0] = __fmul_rn(k, __fsqrt_rn(mean));
+}
+
 // ---------------------------------------------------------------- histogram
 // The bin-count step of histogram_utils._DynamicHistogram1D.add (utils/histogram_utils.py:139-164):
 //   idx = clip(int32(floor((x - lower_bound) / bin_width)), 0, nbins - 1);  counts[idx] += 1
@@ -384,9 +415,18 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
   return count_launch();
 }
 
+size_t mse_workspace_bytes() { return kMseMaxParts * sizeof(double); }
+
 cudaError_t launch_mse_scale_rows(const float* x, long long rows, long long cols, float k,
-                                  float* scale, int sm_count, cudaStream_t st) {
+                                  float* scale, void* ws, int sm_count, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
+  if (rows == 1 && cols > 65536 && ws != nullptr) {
+    int grid = sm_count * 8;
+    if (grid > kMseMaxParts) grid = kMseMaxParts;
+    mse_tensor_partials<<<grid, 256, 0, st>>>(x, cols, static_cast<double*>(ws));
+    mse_tensor_final<<<1, 1, 0, st>>>(static_cast<const double*>(ws), grid, cols, k, scale);
+    return count_launch(2);
+  }
   const int threads = cols >= 16384 ? 1024 : 256;
   long long grid = static_cast<long long>(sm_count) * (threads == 1024 ? 2 : 8);
   if (grid > rows) grid = rows;

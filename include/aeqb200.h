@@ -191,9 +191,11 @@ AEQB_API int aeqb_octav_clip_blocks_f32(const float* x, int64_t rows, int64_t co
                                         int early_stop, float* clip, void* ws, void* stream);
 
 /* scale[r] = k * sqrt(mean(x[r, :]^2)), mse.get_tensor_quant_params
- * (algorithms/uniform_quantize/mse.py:100-108); rows == 1 gives the per-tensor scale. */
+ * (algorithms/uniform_quantize/mse.py:100-108); rows == 1 gives the per-tensor scale.
+ *   ws: aeqb_mse_workspace_bytes() bytes, or NULL (a whole-tensor reduction then runs on one CTA). */
+AEQB_API size_t aeqb_mse_workspace_bytes(void);
 AEQB_API int aeqb_mse_scale_rows_f32(const float* x, int64_t rows, int64_t cols, float k,
-                                     float* scale, void* stream);
+                                     float* scale, void* ws, void* stream);
 
 /* out = x.reshape(-1, n) @ (H_n / sqrt(n)) over the last axis,
  * hadamard_rotation._rotate_with_diagonal_hadamard

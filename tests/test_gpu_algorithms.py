@@ -242,3 +242,31 @@ def test_registry_reaches_new_algorithms(cuda):
     params = [t for t in out if t.tensor_name == "weight"][0].consumers[0].parameters
     np.testing.assert_allclose(params.scale, ref["scale"], rtol=2e-6)
     _assert_ints(params.quantized_data, ref["q"], frac=2e-3)
+
+
+def test_tensorwise_large_groups(cuda):
+  """TENSORWISE on tensors past the single-CTA cut-over (grid-wide reductions per iteration):
+  OCTAV and MSE constants vs the oracle, odd sizes and an unaligned view included."""
+  import torch
+  from aeq_b200 import device
+  from aeq_b200.algorithms.uniform_quantize import mse, octav
+  for shape, idx in (((256, 4096), 1), ((37, 4099), 2)):
+    w = O.synthetic_weight(*shape, index=idx)
+    w[0, :7] = 0.0
+    for bits in (4, 8):
+      with np.errstate(all="ignore"):
+        want = O.octav_clip(w, bits, (0, 1))
+      got = device.octav_clip_rows(torch.from_numpy(w).to(cuda).reshape(1, -1), bits).cpu().numpy()
+      np.testing.assert_allclose(got.reshape(-1), want.reshape(-1), rtol=1e-6)
+      r = _run(octav, w, _cfg(bits, -1))
+      ref = O.octav_requant(w, bits, per_channel=False)
+      np.testing.assert_allclose(r.scale, ref["scale"], rtol=1e-6)
+      _assert_ints(r.quantized_data, ref["q"])
+      rm = _run(mse, w, _cfg(bits, -1))
+      refm = O.mse_requant(w, bits, per_channel=False)
+      np.testing.assert_allclose(rm.scale, refm["scale"], rtol=1e-6)
+      _assert_ints(rm.quantized_data, refm["q"])
+  flat = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), O.synthetic_weight(64, 2048, 9).reshape(-1)])).to(cuda)
+  view = flat[1:].reshape(1, -1)  # 4-byte aligned only
+  want = O.octav_clip(flat[1:].cpu().numpy().reshape(64, 2048), 4, (0, 1))
+  np.testing.assert_allclose(device.octav_clip_rows(view, 4).cpu().numpy().reshape(-1), want.reshape(-1), rtol=1e-6)

@@ -76,7 +76,7 @@ def main():
   cases.append(("requant_blocks32 int4 packed +clip", lambda i: lib.aeqb_requant_blocks_f32(
       P(ws_in[i % NT]), R, C, 32, 4, P(clip_b), None, P(pk), None, P(bscale), st), n * 4.5625))
   cases.append(("mse_scale_rows", lambda i: lib.aeqb_mse_scale_rows_f32(
-      P(ws_in[i % NT]), R, C, 0.05408, P(scale), st), n * 4))
+      P(ws_in[i % NT]), R, C, 0.05408, P(scale), None, st), n * 4))
   cases.append(("quantize (given scale) int8", lambda i: lib.aeqb_quantize_f32(
       P(ws_in[i % NT]), n, R, C, P(scale), None, 1, 8, 1, P(q), st), n * 5))
   cases.append((f"hadamard_rows n={C}", lambda i: lib.aeqb_hadamard_rows_f32(
