@@ -124,6 +124,13 @@ cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols,
 
 // GPTQ (gptq_hessian.cu, gptq_quantize.cu).
 size_t xtx_workspace_bytes(long long T, long long K, int sm_count);
+// tcgen05 3xTF32 path (xtx_tc.cu); *flag_out: device int, non-zero when the input held
+// non-finite values and `out` was left untouched.
+bool xtx_tc_eligible(long long T, long long K);
+size_t xtx_tc_workspace_bytes(long long T, long long K);
+template <typename OutT>
+cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha, OutT* out,
+                          void* ws, int sm_count, const int** flag_out, cudaStream_t st);
 cudaError_t launch_xtx_f64(const float* x, long long T, long long K, double alpha, double* out,
                            void* ws, int sm_count, cudaStream_t st);
 cudaError_t launch_xtx_f32(const float* x, long long T, long long K, double alpha, float* out,

@@ -20,6 +20,8 @@
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
+#include <stdlib.h>
+
 namespace aeqb {
 
 namespace {
@@ -44,9 +46,12 @@ __device__ __forceinline__ void tri_index(int t, int nb, int& bi, int& bj) {
 template <typename OutT>
 __global__ void __launch_bounds__(256)
     xtx_tile(const float* __restrict__ X, long long T, int K, double alpha, OutT* __restrict__ out,
-             float* __restrict__ part, long long t_per_split) {
+             float* __restrict__ part, long long t_per_split, const int* __restrict__ gate) {
   __shared__ __align__(16) float As[2][XK][XT];
   __shared__ __align__(16) float Bs[2][XK][XT];
+  // gate: set by the tensor-core path when its input held non-finite values; only then does this
+  // launch (queued right behind it) do any work.
+  if (gate != nullptr && *gate == 0) return;
   const int nb = (K + XT - 1) / XT;
   int bi, bj;
   tri_index(blockIdx.x, nb, bi, bj);
@@ -423,6 +428,19 @@ __global__ void __launch_bounds__(256)
     out[i] = __ddiv_rn(__dadd_rn(__dmul_rn(a[i], wa), __dmul_rn(b[i], wb)), tot);  // no FMA contraction
 }
 
+// AEQB_XTX_SIMT=1 keeps the contractions on the SIMT kernel (A/B timing, debugging);
+// AEQB_XTX_TC_MIN_GFLOP overrides the size (2*T*K*K, default 8 GFLOP) from which the tcgen05
+// path is taken: below it the split/transpose + tile-quantisation overheads lose to SIMT
+// (measured: 4096 x 512 -> 52 us SIMT vs 142 us, 4100 x 1028 -> 259 us SIMT vs 152 us).
+bool use_tensor_cores(long long T, long long K) {
+  const char* e = getenv("AEQB_XTX_SIMT");
+  if (e && e[0] == '1') return false;
+  if (!xtx_tc_eligible(T, K)) return false;
+  double min_gflop = 8.0;
+  if (const char* m = getenv("AEQB_XTX_TC_MIN_GFLOP")) min_gflop = atof(m);
+  return 2.0 * static_cast<double>(T) * static_cast<double>(K) * static_cast<double>(K) >= min_gflop * 1e9;
+}
+
 int xtx_splits(long long T, int K, int sm_count) {
   const int nb = (K + XT - 1) / XT;
   const long long tiles = static_cast<long long>(nb) * (nb + 1) / 2;
@@ -434,21 +452,40 @@ int xtx_splits(long long T, int K, int sm_count) {
   return static_cast<int>(want);
 }
 
+size_t xtx_split_workspace_bytes(long long T, long long K, int sm_count) {
+  const int s = xtx_splits(T, static_cast<int>(K), sm_count);
+  return s <= 1 ? 0 : static_cast<size_t>(s) * K * K * sizeof(float);
+}
+
 template <typename OutT>
 cudaError_t xtx_impl(const float* x, long long T, long long K, double alpha, OutT* out, void* ws,
-                     int sm_count, cudaStream_t st) {
+                     size_t ws_bytes, int sm_count, cudaStream_t st) {
   if (K <= 0) return cudaSuccess;
   const int k = static_cast<int>(K);
   const int nb = (k + XT - 1) / XT;
   const unsigned tiles = static_cast<unsigned>(static_cast<long long>(nb) * (nb + 1) / 2);
-  const int splits = ws ? xtx_splits(T, k, sm_count) : 1;
+  // Large contractions: tcgen05 3xTF32 (xtx_tc.cu), then this file's SIMT kernel gated on the
+  // "input was not finite" flag so that inf / NaN propagate exactly like sgemm's.
+  if (ws && use_tensor_cores(T, K) && ws_bytes >= xtx_tc_workspace_bytes(T, K) &&
+      reinterpret_cast<uintptr_t>(ws) % 16 == 0) {
+    const int* gate = nullptr;
+    cudaError_t e = launch_xtx_tc<OutT>(x, T, K, alpha, out, ws, sm_count, &gate, st);
+    if (e == cudaSuccess) {
+      xtx_tile<OutT><<<dim3(tiles, 1), 256, 0, st>>>(x, T, k, alpha, out, nullptr, T, gate);
+      return count_launch();
+    }
+    if (e != cudaErrorNotSupported) return e;
+    (void)cudaGetLastError();
+  }
+  const size_t split_need = xtx_split_workspace_bytes(T, K, sm_count);
+  const int splits = (ws && split_need > 0 && ws_bytes >= split_need) ? xtx_splits(T, k, sm_count) : 1;
   if (splits <= 1) {
-    xtx_tile<OutT><<<dim3(tiles, 1), 256, 0, st>>>(x, T, k, alpha, out, nullptr, T > 0 ? T : 1);
+    xtx_tile<OutT><<<dim3(tiles, 1), 256, 0, st>>>(x, T, k, alpha, out, nullptr, T > 0 ? T : 1, nullptr);
     return count_launch();
   }
   long long per = (T + splits - 1) / splits;
   per = (per + XK - 1) / XK * XK;
-  xtx_tile<OutT><<<dim3(tiles, splits), 256, 0, st>>>(x, T, k, alpha, out, static_cast<float*>(ws), per);
+  xtx_tile<OutT><<<dim3(tiles, splits), 256, 0, st>>>(x, T, k, alpha, out, static_cast<float*>(ws), per, nullptr);
   xtx_reduce<OutT><<<sm_count * 4, 256, 0, st>>>(static_cast<const float*>(ws), splits, k, alpha, out);
   return count_launch(2);
 }
@@ -457,23 +494,32 @@ cudaError_t xtx_impl(const float* x, long long T, long long K, double alpha, Out
 
 size_t xtx_workspace_bytes(long long T, long long K, int sm_count) {
   if (K <= 0) return 0;
-  const int s = xtx_splits(T, static_cast<int>(K), sm_count);
-  return s <= 1 ? 0 : static_cast<size_t>(s) * K * K * sizeof(float);
+  if (use_tensor_cores(T, K)) return xtx_tc_workspace_bytes(T, K);
+  return xtx_split_workspace_bytes(T, K, sm_count);
 }
 
 cudaError_t launch_xtx_f64(const float* x, long long T, long long K, double alpha, double* out,
                            void* ws, int sm_count, cudaStream_t st) {
-  return xtx_impl<double>(x, T, K, alpha, out, ws, sm_count, st);
+  return xtx_impl<double>(x, T, K, alpha, out, ws, ws ? xtx_workspace_bytes(T, K, sm_count) : 0,
+                          sm_count, st);
 }
 
 cudaError_t launch_xtx_f32(const float* x, long long T, long long K, double alpha, float* out,
                            void* ws, int sm_count, cudaStream_t st) {
-  return xtx_impl<float>(x, T, K, alpha, out, ws, sm_count, st);
+  return xtx_impl<float>(x, T, K, alpha, out, ws, ws ? xtx_workspace_bytes(T, K, sm_count) : 0,
+                         sm_count, st);
 }
 
-// ws: A (K*K doubles) | L32 (K*K floats) | Y (K*K floats) | info (int, 256 B slot)
+// ws: [ A (K*K doubles) | L32 (K*K floats) ] (dead by the time H^-1 = Y^T Y runs, so the same
+// bytes, grown to what that contraction wants, are its workspace) | Y (K*K floats) | info (256 B)
+static size_t hinv_scratch_bytes(long long K) {
+  size_t a = static_cast<size_t>(K) * K * (sizeof(double) + sizeof(float));
+  const size_t x = xtx_workspace_bytes(K, K, 148);
+  if (x > a) a = x;
+  return (a + 1023) / 1024 * 1024;
+}
 size_t hessian_inverse_workspace_bytes(long long K) {
-  return static_cast<size_t>(K) * K * (sizeof(double) + 2 * sizeof(float)) + 256;
+  return hinv_scratch_bytes(K) + static_cast<size_t>(K) * K * sizeof(float) + 256;
 }
 
 cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, int mutate_diagonal,
@@ -483,10 +529,11 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   const int k = static_cast<int>(K);
   const long long n = K * K;
   unsigned char* p = static_cast<unsigned char*>(ws);
+  const size_t scratch = hinv_scratch_bytes(K);
   double* A = reinterpret_cast<double*>(p);
   float* L32 = reinterpret_cast<float*>(p + n * sizeof(double));
-  float* Y = L32 + n;
-  int* info = reinterpret_cast<int*>(p + n * (sizeof(double) + 2 * sizeof(float)));
+  float* Y = reinterpret_cast<float*>(p + scratch);
+  int* info = reinterpret_cast<int*>(p + scratch + n * sizeof(float));
   int launches = 0;
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
@@ -513,9 +560,7 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   if (e != cudaSuccess) return e;
   // H^-1 = Y^T Y (einsum "ji,jk->ik"): the same contraction as the Hessian itself.  The split
   // workspace may reuse A + L32, which are dead by now.
-  const size_t need = xtx_workspace_bytes(K, K, sm_count);
-  void* xws = need > 0 && need <= static_cast<size_t>(n) * (sizeof(double) + sizeof(float)) ? ws : nullptr;
-  e = xtx_impl<float>(Y, K, K, 1.0, hinv, xws, sm_count, st);
+  e = xtx_impl<float>(Y, K, K, 1.0, hinv, ws, scratch, sm_count, st);
   if (e != cudaSuccess) return e;
   if (info_out) {
     e = cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st);

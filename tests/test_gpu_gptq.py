@@ -55,6 +55,71 @@ def test_hessian_vs_oracle(cuda, tokens, k):
   np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 * np.abs(np.diag(want)).max())
 
 
+@pytest.fixture
+def force_tensor_cores(monkeypatch):
+  """Sends every eligible shape through the tcgen05 3xTF32 path (csrc/xtx_tc.cu); the default
+  threshold (8 GFLOP) would keep oracle-sized cases on the SIMT kernel."""
+  monkeypatch.setenv("AEQB_XTX_TC_MIN_GFLOP", "0")
+  monkeypatch.delenv("AEQB_XTX_SIMT", raising=False)
+
+
+@pytest.mark.parametrize("tokens,k", [
+    (64, 128),       # one tile, two stages, one segment
+    (1000, 256),     # ragged token count (zero-padded plane columns)
+    (2048, 516),     # K % 128 != 0: TMA zero-fills the rows past K, partial float4 columns
+    (777, 1028),     # three column blocks, tiles below the diagonal skipped
+    (40000, 128),    # three token chunks (P accumulated across launches)
+    (4096, 1536),
+])
+def test_hessian_tensor_core_vs_oracle(cuda, force_tensor_cores, tokens, k):
+  """Same bar as the SIMT kernel: |dH| <= 4e-6 * max diag against the oracle's sgemm."""
+  import torch
+  from aeq_b200 import _lib, device
+  x = O.synthetic_activation((2, tokens // 2, k), tokens % 89)
+  x[..., 0] += 0.25  # an all-positive chain: the worst case for a truncating accumulator
+  want = O.gptq_hessian(x)
+  before = _lib.load().aeqb_launch_count()
+  got = device.xtx(torch.from_numpy(x).to(cuda), 2.0 / 2).cpu().numpy()
+  chunks = -(-tokens // 16384)
+  assert _lib.load().aeqb_launch_count() - before == 2 * chunks + 2, "not on the tcgen05 path"
+  np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 * np.abs(np.diag(want)).max())
+  np.testing.assert_array_equal(got, got.T)
+
+
+def test_hessian_tensor_core_nonfinite_gate(cuda, force_tensor_cores):
+  """inf / NaN / 1e38 inputs cannot be split into TF32 planes (inf * 0 = NaN): the device flag
+  routes the whole product to the SIMT kernel, which propagates them like sgemm."""
+  import torch
+  from aeq_b200 import device
+  x = O.synthetic_activation((1, 512, 256), 5)
+  x[0, 3, 7] = np.inf
+  x[0, 100, 9] = np.nan
+  x[0, 200, 11] = 2e38
+  with np.errstate(all="ignore"):
+    want = O.gptq_hessian(x)
+  got = device.xtx(torch.from_numpy(x).to(cuda), 2.0).cpu().numpy()
+  np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+  np.testing.assert_array_equal(np.isinf(got), np.isinf(want))
+  ok = np.isfinite(want)
+  np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=4e-6 * np.abs(want[ok]).max())
+
+
+def test_hessian_inverse_tensor_core(cuda, force_tensor_cores):
+  """H^-1 = L^-T L^-1 through the tcgen05 contraction (K = T = 768)."""
+  import torch
+  from aeq_b200 import device
+  k = 768
+  x = O.synthetic_activation((4, 2 * k, k), 3)
+  h = O.gptq_hessian(x)
+  got = device.hessian_inverse(torch.from_numpy(h.copy()).to(cuda), 0.01).cpu().numpy().astype(np.float64)
+  want = O.gptq_hessian_inverse(h.copy())
+  np.testing.assert_allclose(got, want, rtol=0, atol=1e-4 * np.abs(want).max())
+  d = O.gptq_damped_diagonal(h)
+  hd = h.copy()
+  np.fill_diagonal(hd, d)
+  np.testing.assert_allclose(hd @ got, np.eye(k), rtol=0, atol=2e-3)
+
+
 def test_calibrate_mirror_and_merge(cuda):
   """gptq.calibrate QSVs (gptq_test.py:50-114: +-1e39 filtered from min/max, not from H) and the
   sample-weighted Hessian merge (qsv_utils_test.py:111-180)."""
