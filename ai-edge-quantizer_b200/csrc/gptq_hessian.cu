@@ -16,7 +16,8 @@
 //                 memory, 8x8 register tile per thread, upper-triangular tiles only,
 //                 optional deterministic split over tokens (fixed-order reduce).
 //   chol_panel / chol_syrk   right-looking blocked Cholesky in fp64, block 32.
-//   trtri_diag / trtri_cols  blocked lower-triangular inverse in fp32, block 64.
+//   trtri_diag / trtri_pair_gemm  lower-triangular inverse in fp32: 64 x 64 diagonal blocks,
+//                 then recursive doubling with two batched SGEMMs per level.
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // Inverse of each TB x TB diagonal block (forward substitution, one thread per column),
-// written into the diagonal blocks of Y; the rest of Y's upper triangle is zeroed by trtri_cols.
+// written into the diagonal blocks of Y; the launcher zeroes Y first (the upper triangle stays 0).
 __global__ void __launch_bounds__(TB)
     trtri_diag(const float* __restrict__ L, float* __restrict__ Y, int K) {
   __shared__ float D[TB][TB + 1];
@@ -351,70 +352,122 @@ __global__ void __launch_bounds__(TB)
   }
 }
 
-// Block column j, column slice s (TS columns): for i = j+1 .. : Y[i, js] = -Dinv[i] * sum_{k=j}^{i-1} L[i,k] Y[k, js].
-// One CTA owns its slice top to bottom, so the recurrence needs no grid-wide sync.
-constexpr int TS = 16;
+// Recursive doubling above the diagonal blocks: with Y holding the inverses of all b x b
+// diagonal blocks, the 2b x 2b block [[A, 0], [B, C]] has inverse [[A^-1, 0], [-C^-1 B A^-1, C^-1]].
+// One level is two batched SGEMMs over all block pairs p (rows / columns r0 = 2 b p):
+//   mode 0:  T      = B * A^-1      B = L[r0+b.., r0..r0+b),  A^-1 = Y[r0.., r0..)   (lower tri.)
+//   mode 1:  Y_off  = -C^-1 * T     C^-1 = Y[r0+b.., r0+b..)  (lower triangular)
+// log2(K / 64) levels of fully parallel GEMMs replace the former per-slice recurrence, whose
+// first block column was a chain of 2016 dependent 64 x 64 products (10.9 ms at K = 4096).
+// 128 x 128 tile, 16-deep slabs, 8 x 8 per thread; the triangular operand trims the k range.
+constexpr int GT = 128, GK = 16;
 __global__ void __launch_bounds__(256)
-    trtri_cols(const float* __restrict__ L, float* __restrict__ Y, int K) {
-  __shared__ float Ls[TB][TB + 1];
-  __shared__ float Ys[TB][TS + 1];
-  __shared__ float Ss[TB][TS + 1];
-  const int nblk = (K + TB - 1) / TB;
-  const int j = blockIdx.x / (TB / TS), s = blockIdx.x % (TB / TS);
-  const int cj = j * TB + s * TS;  // first global column of the slice
-  const int tid = threadIdx.x;
-  const int r = tid >> 2, cq = (tid & 3) * 4;  // thread: row r (0..63), 4 columns cq..cq+3
-  // zero the strictly-upper blocks of this slice (rows above block j)
-  for (long long e = tid; e < static_cast<long long>(j) * TB * TS; e += 256) {
-    const int rr = static_cast<int>(e / TS), cc = static_cast<int>(e % TS);
-    if (cj + cc < K) Y[static_cast<long long>(rr) * K + cj + cc] = 0.0f;
+    trtri_pair_gemm(const float* __restrict__ Lm, const float* __restrict__ Ym,
+                    const float* __restrict__ Tin, float* __restrict__ Out, int K, int b, int mode) {
+  __shared__ __align__(16) float As[2][GK][GT + 4];
+  __shared__ __align__(16) float Bs[2][GK][GT];
+  const long long r0 = static_cast<long long>(blockIdx.z) * 2 * b;
+  const int Mp = static_cast<int>(min(static_cast<long long>(b), K - r0 - b));
+  if (Mp <= 0) return;
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  if (i0 >= Mp || j0 >= b) return;
+  const float* A;
+  const float* B;
+  float* C = Out + (r0 + b) * K + r0;
+  int Kd, k_lo, k_hi;
+  float alpha;
+  if (mode == 0) {
+    A = Lm + (r0 + b) * K + r0;   // [Mp, b]
+    B = Ym + r0 * K + r0;         // [b, b] lower triangular: rows k >= column j
+    Kd = b; k_lo = j0; k_hi = b; alpha = 1.0f;
+  } else {
+    A = Ym + (r0 + b) * K + (r0 + b);  // [Mp, Mp] lower triangular: columns k <= row i
+    B = Tin + (r0 + b) * K + r0;       // [Mp, b]
+    Kd = Mp; k_lo = 0; k_hi = min(i0 + GT, Mp); alpha = -1.0f;
   }
-  for (int i = j + 1; i < nblk; ++i) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = j; k < i; ++k) {
-      __syncthreads();
-      for (int e = tid; e < TB * TB; e += 256) {
-        const int rr = e / TB, kk = e % TB;
-        const int gr = i * TB + rr, gc = k * TB + kk;
-        Ls[rr][kk] = (gr < K && gc < K) ? L[static_cast<long long>(gr) * K + gc] : 0.0f;
-      }
-      for (int e = tid; e < TB * TS; e += 256) {
-        const int rr = e / TS, cc = e % TS;
-        const int gr = k * TB + rr, gc = cj + cc;
-        Ys[rr][cc] = (gr < K && gc < K) ? Y[static_cast<long long>(gr) * K + gc] : 0.0f;
-      }
-      __syncthreads();
-#pragma unroll 16
-      for (int kk = 0; kk < TB; ++kk) {
-        const float l = Ls[r][kk];
+  const int N = b;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool vec = (K % 4 == 0) && (reinterpret_cast<uintptr_t>(Lm) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(Ym) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(Tin) % 16 == 0);
+  float acc[8][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fmaf(l, Ys[kk][cq + u], acc[u]);
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0f;
+
+  auto load_slab = [&](int buf, int k0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid * 2 + u;
+      {  // A tile: 128 rows x 16 k, k contiguous in memory -> transposed into As[k][row]
+        const int r = idx >> 2, k4 = (idx & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i0 + r < Mp) {
+          const float* src = A + static_cast<long long>(i0 + r) * K + k0 + k4;
+          if (vec && k0 + k4 + 3 < Kd) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k0 + k4 + e < Kd) v[e] = src[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) As[buf][k4 + e][r] = v[e];
       }
+      {  // B tile: 16 k x 128 columns, columns contiguous
+        const int kr = idx >> 5, c4 = (idx & 31) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + kr < Kd) {
+          const float* src = B + static_cast<long long>(k0 + kr) * K + j0 + c4;
+          if (vec && j0 + c4 + 3 < N) {
+            t = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            float w[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (j0 + c4 + e < N) w[e] = src[e];
+            t = make_float4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[buf][kr][c4]) = t;
+      }
+    }
+  };
+
+  int buf = 0;
+  if (k_lo < k_hi) load_slab(0, k_lo);
+  __syncthreads();
+  for (int k0 = k_lo; k0 < k_hi; k0 += GK) {
+    if (k0 + GK < k_hi) load_slab(buf ^ 1, k0 + GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4 + 64]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4 + 64]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
     }
     __syncthreads();
+    buf ^= 1;
+  }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Ss[r][cq + u] = acc[u];
-    // Dinv[i] (already in Y's diagonal block) into Ls
-    for (int e = tid; e < TB * TB; e += 256) {
-      const int rr = e / TB, kk = e % TB;
-      const int gr = i * TB + rr, gc = i * TB + kk;
-      Ls[rr][kk] = (gr < K && gc < K && kk <= rr) ? Y[static_cast<long long>(gr) * K + gc] : 0.0f;
-    }
-    __syncthreads();
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 16
-    for (int kk = 0; kk < TB; ++kk) {
-      const float d = Ls[r][kk];
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + ty * 4 + (a & 3) + (a >> 2) * 64;
+    if (i >= Mp) continue;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) o[u] = fmaf(d, Ss[kk][cq + u], o[u]);
+    for (int c = 0; c < 8; ++c) {
+      const int j = j0 + tx * 4 + (c & 3) + (c >> 2) * 64;
+      if (j < N) C[static_cast<long long>(i) * K + j] = alpha * acc[a][c];
     }
-    const int gr = i * TB + r;
-    if (gr < K) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (cj + cq + u < K) Y[static_cast<long long>(gr) * K + cj + cq + u] = -o[u];
-    }
-    __syncthreads();  // Y[i, slice] is read back (as Ys) in later iterations of i
   }
 }
 
@@ -554,8 +607,17 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   }
   lower_to_f32<<<cgrid, 256, 0, st>>>(A, L32, k); ++launches;
   const int nblk = (k + TB - 1) / TB;
+  e = cudaMemsetAsync(Y, 0, static_cast<size_t>(n) * sizeof(float), st);  // the upper triangle stays 0
+  if (e != cudaSuccess) return e;
   trtri_diag<<<nblk, TB, 0, st>>>(L32, Y, k); ++launches;
-  trtri_cols<<<nblk * (TB / TS), 256, 0, st>>>(L32, Y, k); ++launches;
+  float* Tbuf = reinterpret_cast<float*>(A);  // the fp64 factor is dead once L32 exists
+  for (long long b = TB; b < K; b *= 2) {
+    const unsigned pairs = static_cast<unsigned>((K + 2 * b - 1) / (2 * b));
+    const unsigned tiles = static_cast<unsigned>((b + GT - 1) / GT);
+    trtri_pair_gemm<<<dim3(tiles, tiles, pairs), 256, 0, st>>>(L32, Y, Tbuf, Tbuf, k, static_cast<int>(b), 0);
+    trtri_pair_gemm<<<dim3(tiles, tiles, pairs), 256, 0, st>>>(L32, Y, Tbuf, Y, k, static_cast<int>(b), 1);
+    launches += 2;
+  }
   e = count_launch(launches);
   if (e != cudaSuccess) return e;
   // H^-1 = Y^T Y (einsum "ji,jk->ik"): the same contraction as the Hessian itself.  The split

@@ -307,6 +307,68 @@ def extra_modes(dev, ws, peak, steps):
       "ms_hessian_inverse": ms_inv, "ms_obs_loop": ms_q,
       "obs_loop_tflops": 1.0 * ROWS * COLS * COLS / ms_q / 1e9,
       "note": "value = fp32 weight bytes / (inverse + OBS loop) for one layer, Hessian given"}
+  del x, h, hinv
+  out.update(config_sets(dev, peak, reps))
+  return out
+
+
+def config_sets(dev, peak, reps):
+  """BASELINE.json configs[2] and the weight side of configs[4] at their own tensor shapes
+  (SURVEY.md §8d): the Gemma-2B FC set through INT4 block-32, the Llama-7B FC set through INT8 /
+  INT4 per-channel (11008-wide rows take the rows kernel's 64 KiB stage class)."""
+  import torch
+  from aeq_b200 import device
+  out = {}
+
+  def make(shapes, layers):
+    g = torch.Generator(device=dev).manual_seed(4242)
+    ws = []
+    for _ in range(layers):
+      for r, c in shapes:
+        w = torch.randn(r, c, device=dev, generator=g) * 0.02
+        w.view(-1)[::1024] *= 20.0
+        ws.append(w)
+    return ws
+
+  def timeit(fn):
+    for _ in range(2):
+      fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+  gemma = [(2048, 2048), (2048, 2048), (256, 2048), (256, 2048), (16384, 2048), (16384, 2048), (2048, 16384)]
+  ws = make(gemma, 18)
+  n_bytes = sum(w.numel() for w in ws) * 4
+  st = {}
+
+  def g4():
+    st["o"] = device.requant_blocks_batch(ws, 32, 4, outs=st.get("o"))
+  ms = timeit(g4)
+  out["cfg3_gemma2b_int4_block32_packed"] = {
+      "value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": len(ws), "fp32_bytes": n_bytes,
+      "bytes_per_weight": 4.5625, "roofline_frac": (n_bytes / 4) * 4.5625 / ms / 1e6 / peak}
+  del ws, st
+
+  llama = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+  ws = make(llama, 4)
+  n_bytes = sum(w.numel() for w in ws) * 4
+  for bits, bpw in ((8, 5.0), (4, 4.5)):
+    st = {}
+
+    def rows():
+      st["o"] = device.requant_rows_batch(ws, bits, True, want_q=(bits == 8), want_packed=(bits == 4),
+                                           outs=st.get("o"))
+    ms = timeit(rows)
+    out[f"cfg5_llama7b_int{bits}_perchannel"] = {
+        "value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": len(ws), "fp32_bytes": n_bytes,
+        "bytes_per_weight": bpw, "roofline_frac": (n_bytes / 4) * bpw / ms / 1e6 / peak}
+    del st
   return out
 
 
