@@ -12,6 +12,8 @@ import functools
 
 from . import algorithm_manager_api
 from . import qtyping
+from .algorithms.nonlinear_quantize import float_casting
+from .algorithms.uniform_quantize import dequantized_weight_recovery
 from .algorithms.uniform_quantize import gptq
 from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
@@ -116,3 +118,17 @@ register_quantized_op(
     update_qsv_func=qsv_utils.gptq_and_moving_average_update)
 register_op_quant_config_validation_func(AlgorithmName.GPTQ, _check_config)
 register_config_check_policy_func(AlgorithmName.GPTQ, None)
+
+# Recovery of QAT (fake-quantised) weights: activations calibrate like min-max
+# (algorithm_manager.py:272-293 binds dequantized_weight_recovery.calibrate / init_qsvs).
+register_weight_algorithm(AlgorithmName.DEQUANTIZED_WEIGHT_RECOVERY,
+                          dequantized_weight_recovery.get_tensor_quant_params,
+                          dequantized_weight_recovery.calibrate)
+# fp16 weights behind DEQUANTIZE: no calibration, no statistics (algorithm_manager.py:242-269).
+for _op in sorted(float_casting.SUPPORTED_WEIGHT_QUANT_OPS, key=lambda o: o.value):
+  register_quantized_op(
+      AlgorithmName.FLOAT_CASTING, _op, _init_qsvs, calibration_func=None,
+      materialize_func=float_casting.materialize_weight_op)
+register_op_quant_config_validation_func(AlgorithmName.FLOAT_CASTING,
+                                         float_casting.check_op_quantization_config)
+register_config_check_policy_func(AlgorithmName.FLOAT_CASTING, None)

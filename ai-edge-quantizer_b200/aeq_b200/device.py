@@ -451,3 +451,38 @@ def hist_accumulate(x: torch.Tensor, lower_bound: float, bin_width: float, nbins
   _lib.call("aeqb_hist_accumulate_f32", _ptr(x), x.numel(), float(lower_bound), float(bin_width),
             int(nbins), int(finite_only), _ptr(counts), _stream())
   return counts
+
+
+def dwr_scales(x: torch.Tensor, n_groups: int, group_len: int) -> torch.Tensor:
+  """fp32 [n_groups]: smallest step > 1e-9 of sort(|group| U {0}), floored at 1e-9
+  (aeqb_dwr_scales_f32; dequantized_weight_recovery.py:132-217)."""
+  if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+    raise ValueError("expected a contiguous float32 CUDA tensor")
+  if x.numel() != n_groups * group_len:
+    raise ValueError(f"{x.numel()} values do not form {n_groups} groups of {group_len}")
+  scale = torch.empty(n_groups, dtype=torch.float32, device=x.device)
+  n = _lib.load().aeqb_dwr_workspace_bytes(n_groups, group_len)
+  ws = torch.empty(n, dtype=torch.uint8, device=x.device) if n else None
+  _lib.call("aeqb_dwr_scales_f32", _ptr(x), n_groups, group_len, _ptr(scale), _ptr(ws), _stream())
+  return scale
+
+
+def max_abs_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+  """fp32 [1] = max |a - b| (aeqb_max_abs_diff_f32)."""
+  if a.dtype != torch.float32 or b.dtype != torch.float32 or a.numel() != b.numel():
+    raise ValueError("expected two float32 tensors of equal size")
+  a, b = a.contiguous(), b.contiguous()
+  out = torch.empty(1, dtype=torch.float32, device=a.device)
+  ws = torch.empty(8, dtype=torch.uint8, device=a.device)
+  _lib.call("aeqb_max_abs_diff_f32", _ptr(a), _ptr(b), a.numel(), _ptr(out), _ptr(ws), _stream())
+  return out
+
+
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+  """float16 copy, round to nearest even (aeqb_cast_f32_f16; float_casting.py:160-162)."""
+  if not x.is_cuda or x.dtype != torch.float32:
+    raise ValueError("expected a float32 CUDA tensor")
+  x = x.contiguous()
+  out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+  _lib.call("aeqb_cast_f32_f16", _ptr(x), x.numel(), _ptr(out), _stream())
+  return out

@@ -18,6 +18,7 @@ from __future__ import annotations
 import functools
 
 from . import qtyping as _qt
+from .algorithms.uniform_quantize import dequantized_weight_recovery
 from .algorithms.uniform_quantize import gptq
 from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
@@ -36,6 +37,9 @@ _BINDINGS = {
             "naive_min_max_quantize"),
     "GPTQ": ("_GPTQ_OP_NAME_MATERIALIZE_FUNC_DICT", gptq.get_tensor_quant_params,
              "naive_min_max_quantize"),
+    "dequantized_weight_recovery": ("DEQUANTIZED_WEIGHT_RECOVERY_OP_NAME_MATERIALIZE_FUNC_DICT",
+                                    dequantized_weight_recovery.get_tensor_quant_params,
+                                    "dequantized_weight_recovery"),
 }
 
 # Algorithms whose reference materialisers call their module's own

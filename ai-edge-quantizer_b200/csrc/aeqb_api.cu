@@ -451,4 +451,37 @@ int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* str
                "aeqb_pack_bits");
 }
 
+size_t aeqb_dwr_workspace_bytes(int64_t n_groups, int64_t group_len) {
+  return (n_groups > 0 && group_len > 0) ? aeqb::dwr_workspace_bytes(n_groups, group_len) : 0;
+}
+
+int aeqb_dwr_scales_f32(const float* x, int64_t n_groups, int64_t group_len, float* scale, void* ws,
+                        void* stream) {
+  if (n_groups < 0 || group_len <= 0) return fail("bad group shape [%lld x %lld]", (long long)n_groups, (long long)group_len);
+  if (n_groups == 0) return 0;
+  if (!x || !scale) return fail("x / scale are NULL");
+  if (group_len > 16384 && n_groups != 1)
+    return fail("groups longer than 16384 values are supported for a single group only, got %lld groups of %lld",
+                (long long)n_groups, (long long)group_len);
+  if (group_len > 16384 && !ws) return fail("ws is NULL (aeqb_dwr_workspace_bytes)");
+  return check(aeqb::launch_dwr_scales(x, n_groups, group_len, scale, ws, sm_count(),
+                                       static_cast<cudaStream_t>(stream)),
+               "aeqb_dwr_scales_f32");
+}
+
+int aeqb_max_abs_diff_f32(const float* a, const float* b, int64_t n, float* out, void* ws, void* stream) {
+  if (n < 0) return fail("bad length %lld", (long long)n);
+  if (!out || !ws) return fail("out / ws are NULL");
+  if (n > 0 && (!a || !b)) return fail("a / b are NULL");
+  return check(aeqb::launch_max_abs_diff(a, b, n, out, ws, sm_count(), static_cast<cudaStream_t>(stream)),
+               "aeqb_max_abs_diff_f32");
+}
+
+int aeqb_cast_f32_f16(const float* x, int64_t n, uint16_t* out, void* stream) {
+  if (n < 0) return fail("bad length %lld", (long long)n);
+  if (n > 0 && (!x || !out)) return fail("x / out are NULL");
+  return check(aeqb::launch_cast_f16(x, n, out, sm_count(), static_cast<cudaStream_t>(stream)),
+               "aeqb_cast_f32_f16");
+}
+
 }  // extern "C"

@@ -156,6 +156,13 @@ cudaError_t launch_quantize(const float* x, long long n, long long channels, lon
 cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long channels,
                               long long inner, const float* scale, const int32_t* zp, int pstride,
                               int wrap8, float* out, int sm_count, cudaStream_t st);
+// recovery.cu
+size_t dwr_workspace_bytes(long long n_groups, long long glen);
+cudaError_t launch_dwr_scales(const float* x, long long n_groups, long long glen, float* scale,
+                              void* ws, int sm_count, cudaStream_t st);
+cudaError_t launch_max_abs_diff(const float* a, const float* b, long long n, float* out, void* ws,
+                                int sm_count, cudaStream_t st);
+cudaError_t launch_cast_f16(const float* x, long long n, void* out, int sm_count, cudaStream_t st);
 cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, int sm_count,
                         cudaStream_t st);
 

@@ -274,6 +274,26 @@ AEQB_API int aeqb_dequantize_f32(const void* q, int q_bytes, int64_t n, int64_t 
  * lowest), odd tail zero padded.  out: ceil(n*bits/8) bytes.  bits 2 or 4. */
 AEQB_API int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* stream);
 
+/* ---------------------------------------------------------------- recovery / casting
+ * dequantized_weight_recovery.get_zp_scale_from_dequantized_symmetric_weights
+ * (algorithms/uniform_quantize/dequantized_weight_recovery.py:132-217): for each of n_groups
+ * groups of group_len consecutive floats (a row, a block, or the whole tensor as one group)
+ * scale = max(smallest difference > 1e-9 between neighbours of sort(|x| U {0}), 1e-9);
+ * 1e-9 when all values coincide.  group_len <= 16384, or n_groups == 1 with
+ * ws = aeqb_dwr_workspace_bytes(1, group_len) bytes (radix-sort path). */
+AEQB_API size_t aeqb_dwr_workspace_bytes(int64_t n_groups, int64_t group_len);
+AEQB_API int aeqb_dwr_scales_f32(const float* x, int64_t n_groups, int64_t group_len, float* scale,
+                                 void* ws, void* stream);
+
+/* out[0] = max |a[i] - b[i]| (NaN propagates): the check of
+ * dequantized_weight_recovery._validate_recovered_weights (:36-63).  ws: 8 bytes. */
+AEQB_API int aeqb_max_abs_diff_f32(const float* a, const float* b, int64_t n, float* out, void* ws,
+                                   void* stream);
+
+/* weight.astype(np.float16), round to nearest even, overflow to inf:
+ * float_casting.materialize_fc_conv (algorithms/nonlinear_quantize/float_casting.py:160-162). */
+AEQB_API int aeqb_cast_f32_f16(const float* x, int64_t n, uint16_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -442,6 +442,56 @@ def gptq_requant(w, hessian, bits: int, symmetric: bool = True, block: int = 0,
 
 
 # --------------------------------------------------------------------------
+# §8(f) row 3: dequantized_weight_recovery / float_casting
+# --------------------------------------------------------------------------
+def dwr_group_scales(groups: np.ndarray, min_scale: float = 1e-9) -> np.ndarray:
+  """One recovered scale per row of `groups` [n_groups, group_len]
+  (dequantized_weight_recovery.py:181-209): sort |x| with a 0 appended, smallest
+  adjacent difference > 1e-9, floored at min_scale; min_scale when all equal."""
+  a = np.abs(groups)
+  a = np.hstack([a, np.zeros((a.shape[0], 1), dtype=a.dtype)])
+  d = np.diff(np.sort(a, axis=1), axis=1)
+  m = np.min(np.where(d > 1e-9, d, np.inf), axis=1)
+  s = np.maximum(m, min_scale)
+  s[s == np.inf] = min_scale
+  return s
+
+
+def dwr_requant(w: np.ndarray, bits: int, block: int = 0, per_channel: bool = True):
+  """scale / zero_point / q of dequantized_weight_recovery.get_tensor_quant_params
+  (:220-262) for a 2-D FC weight (quantised dim 0, blocks along dim 1)."""
+  if block:
+    scale = dwr_group_scales(w.reshape(-1, block)).reshape(w.shape[0], w.shape[1] // block)
+  elif per_channel:
+    scale = dwr_group_scales(w).reshape(w.shape[0], 1)
+  else:
+    u = np.unique(np.append(np.abs(np.ravel(w)), 0))  # _get_scale (:66-77)
+    v = float(np.maximum(np.min(np.diff(u)), 1e-9)) if u.size > 1 else 1e-9
+    scale = np.array([[v]])
+  zp = np.zeros_like(scale, dtype=np.int32)
+  q = quantize(w, scale, zp, bits, True, block)
+  return {"scale": scale, "zero_point": zp, "q": q}
+
+
+def float_cast(w: np.ndarray) -> np.ndarray:
+  """float_casting.materialize_fc_conv's weight (float_casting.py:160-162)."""
+  return w.astype(np.float16)
+
+
+def fake_quantized_weight(rows: int, cols: int, bits: int, block: int = 0, index: int = 0,
+                          per_channel: bool = True) -> np.ndarray:
+  """A QAT-style weight: integers in the signed range times a per-group fp32 scale."""
+  rng = np.random.default_rng(3000 + index)
+  lo, hi = int(qrange(bits)[0]) + 1, int(qrange(bits)[1])
+  q = rng.integers(lo, hi + 1, size=(rows, cols)).astype(F32)
+  if block:
+    s = rng.uniform(0.001, 0.05, size=(rows, cols // block)).astype(F32)
+    return (q.reshape(rows, cols // block, block) * s[:, :, None]).reshape(rows, cols).astype(F32)
+  s = rng.uniform(0.001, 0.05, size=(rows, 1) if per_channel else (1, 1)).astype(F32)
+  return (q * s).astype(F32)
+
+
+# --------------------------------------------------------------------------
 # a13 / a14: bit packing and the serialised blockwise scale
 #            (transformations/transformation_utils.py:293-353,
 #             transformations/quantize_tensor.py:107-147)

@@ -62,7 +62,7 @@ def main():
   for name, fn in (("minmax", gen_minmax), ("octav", gen_octav), ("mse", gen_mse),
                    ("hadamard", gen_hadamard), ("gptq", gen_gptq),
                    ("calibration", gen_calibration), ("pack", gen_pack),
-                   ("histogram", gen_histogram)):
+                   ("histogram", gen_histogram), ("recovery", gen_recovery)):
     if not only or name in only:
       fn()
 
@@ -198,6 +198,26 @@ def gen_calibration():
   out["ema_min"], out["ema_max"] = q["min"], q["max"]
   save("calibration", **out)
 
+
+
+def gen_recovery():
+  """dequantized_weight_recovery on QAT-style weights (every granularity) + the fp16 cast."""
+  DWR = refshim.ref("algorithms.uniform_quantize.dequantized_weight_recovery")
+  out = {}
+  cases = []
+  for i, (bits, gk, shape) in enumerate([(4, 0, (16, 512)), (8, 0, (8, 11008)), (4, 32, (16, 512)),
+                                         (8, 256, (8, 1024)), (4, -1, (16, 512)), (8, -1, (32, 1024))]):
+    w = O.fake_quantized_weight(shape[0], shape[1], bits, block=max(gk, 0), index=i, per_channel=(gk == 0))
+    w[1, :] = 0.0
+    w[2, :] = w[2, 0]
+    r = run(DWR, w, cfg(bits, True, gk))
+    out[f"w{i}"], out[f"scale{i}"], out[f"q{i}"] = w, r.scale, r.quantized_data
+    cases.append((bits, gk))
+  out["cases"] = np.array(cases)
+  w = weight(32, 300, 77)
+  w[5, 0], w[5, 1], w[5, 2] = 70000.0, -65520.0, 6e-8  # overflow to inf, the rounding boundary, a subnormal
+  out["cast_in"], out["cast_out"] = w, w.astype(np.float16)
+  save("recovery", **out)
 
 
 def gen_pack():

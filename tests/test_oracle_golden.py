@@ -272,3 +272,15 @@ def test_pack_fixtures_bit_exact():
   g = gold("pack")
   for bits, n in ((4, 15), (4, 4096), (2, 13), (2, 1024)):
     np.testing.assert_array_equal(O.pack_bits(bits, g[f"b{bits}_n{n}_in"]), g[f"b{bits}_n{n}_out"])
+
+
+def test_recovery_fixtures_bit_exact():
+  """dequantized_weight_recovery + float_casting fixtures (tests/golden/recovery.npz)."""
+  z = np.load(os.path.join(GOLD, "recovery.npz"))
+  for i, (bits, gk) in enumerate(z["cases"]):
+    o = O.dwr_requant(z[f"w{i}"], int(bits), block=max(int(gk), 0), per_channel=(gk == 0))
+    np.testing.assert_array_equal(o["scale"], z[f"scale{i}"])
+    assert o["scale"].dtype == z[f"scale{i}"].dtype
+    np.testing.assert_array_equal(o["q"], z[f"q{i}"])
+  with np.errstate(all="ignore"):
+    np.testing.assert_array_equal(O.float_cast(z["cast_in"]).view(np.uint16), z["cast_out"].view(np.uint16))

@@ -129,3 +129,29 @@ def test_pack(R, bits, n):
   half = 2 ** (bits - 1)
   v = np.random.default_rng(n).integers(-half, half, n, dtype=np.int8)
   np.testing.assert_array_equal(O.pack_bits(bits, v), R.tu.pack_data(bits, v.view(np.uint8).copy()))
+
+
+# ---- §8(f) row 3: dequantized_weight_recovery / float_casting -------------------------------
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("gk", [0, -1, 32, 128])
+def test_dequantized_weight_recovery(R, bits, gk):
+  dwr = refshim.ref("algorithms.uniform_quantize.dequantized_weight_recovery")
+  w = O.fake_quantized_weight(24, 256, bits, block=max(gk, 0), index=bits + gk % 7, per_channel=(gk == 0))
+  w[1, :] = 0.0          # all equal -> min_scale
+  w[2, :] = w[2, 0]      # a single non-zero value: its distance to the appended 0
+  r = _run(R, dwr, w, bits, True, gk)
+  o = O.dwr_requant(w, bits, block=max(gk, 0), per_channel=(gk == 0))
+  np.testing.assert_array_equal(o["scale"], r.scale)
+  assert o["scale"].dtype == r.scale.dtype and o["scale"].shape == r.scale.shape
+  np.testing.assert_array_equal(o["zero_point"], r.zero_point)
+  np.testing.assert_array_equal(o["q"], r.quantized_data)
+
+
+def test_dequantized_weight_recovery_literal(R):
+  """dequantized_weight_recovery_test.py: the per-tensor / per-channel literal vectors."""
+  dwr = refshim.ref("algorithms.uniform_quantize.dequantized_weight_recovery")
+  deq = np.array([[-0.5, 0.25, 1.0], [0.75, -1.25, 0.5]], dtype=np.float32)
+  zp, sc = dwr.get_zp_scale_from_dequantized_symmetric_weights(deq, None)
+  np.testing.assert_array_equal(O.dwr_requant(deq, 8, per_channel=False)["scale"], sc)
+  zp, sc = dwr.get_zp_scale_from_dequantized_symmetric_weights(deq, 0)
+  np.testing.assert_array_equal(O.dwr_group_scales(deq).reshape(2, 1), sc)
