@@ -66,6 +66,14 @@ SIGNATURES = {
     "aeqb_dwr_scales_f32": (_I, [_P, _L, _L, _P, _P, _P]),
     "aeqb_max_abs_diff_f32": (_I, [_P, _P, _L, _P, _P, _P]),
     "aeqb_cast_f32_f16": (_I, [_P, _L, _P, _P]),
+    "aeqb_colsq_workspace_bytes": (_c.c_size_t, [_L, _L]),
+    "aeqb_colsq_f64": (_I, [_P, _L, _L, _D, _P, _P, _P]),
+    "aeqb_oscar_pass_workspace_bytes": (_c.c_size_t, [_L, _L, _L]),
+    "aeqb_oscar_pass_f32": (_I, [_P, _L, _L, _L, _P, _P, _P, _P, _P]),
+    "aeqb_oscar_clip_workspace_bytes": (_c.c_size_t, [_L, _L, _L]),
+    "aeqb_oscar_clip_f32": (_I, [_P, _L, _L, _L, _P, _P, _P, _D, _I, _P, _P, _P]),
+    "aeqb_oscar_scale_f64": (_I, [_P, _L, _I, _I, _P, _P]),
+    "aeqb_oscar_quantize_f32": (_I, [_P, _L, _L, _L, _P, _P, _I, _P, _P]),
 }
 
 

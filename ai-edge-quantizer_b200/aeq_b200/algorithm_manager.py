@@ -19,6 +19,7 @@ from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
 from .algorithms.uniform_quantize import octav
+from .algorithms.uniform_quantize import oscar
 from .algorithms.utils import common_utils
 from .utils import qsv_utils
 
@@ -109,6 +110,11 @@ register_weight_algorithm(AlgorithmName.MSE, mse.get_tensor_quant_params,
 register_weight_algorithm(AlgorithmName.HADAMARD_ROTATION,
                           hadamard_rotation.get_tensor_quant_params,
                           naive_min_max_quantize.min_max_calibrate)
+# Same weight arithmetic; the variants differ only in the activation-side transformation the
+# reference's materialisers add (INSERT_DECOMPOSED_HADAMARD_ROTATION, hadamard_rotation.py:283).
+register_weight_algorithm(AlgorithmName.DECOMPOSED_HADAMARD_ROTATION,
+                          hadamard_rotation.get_tensor_quant_params,
+                          naive_min_max_quantize.min_max_calibrate)
 # GPTQ: FULLY_CONNECTED only in the reference (algorithm_manager.py:434-455); the activation
 # QSV carries the Hessian and merges by sample-weighted mean.
 register_quantized_op(
@@ -132,3 +138,12 @@ for _op in sorted(float_casting.SUPPORTED_WEIGHT_QUANT_OPS, key=lambda o: o.valu
 register_op_quant_config_validation_func(AlgorithmName.FLOAT_CASTING,
                                          float_casting.check_op_quantization_config)
 register_config_check_policy_func(AlgorithmName.FLOAT_CASTING, None)
+
+# OSCAR: FULLY_CONNECTED only, its own materialiser (INSERT_MULTIPLY on the activation) and the
+# mu2-carrying QSV merge (algorithm_manager.py:453-480).
+register_quantized_op(
+    AlgorithmName.OSCAR, _Op.FULLY_CONNECTED, _init_qsvs, calibration_func=oscar.calibrate,
+    materialize_func=oscar.materialize_fully_connected,
+    update_qsv_func=qsv_utils.oscar_and_moving_average_update)
+register_op_quant_config_validation_func(AlgorithmName.OSCAR, _check_config)
+register_config_check_policy_func(AlgorithmName.OSCAR, None)

@@ -486,3 +486,70 @@ def cast_f16(x: torch.Tensor) -> torch.Tensor:
   out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
   _lib.call("aeqb_cast_f32_f16", _ptr(x), x.numel(), _ptr(out), _stream())
   return out
+
+
+# ---------------------------------------------------------------- OSCAR (float64, csrc/oscar.cu)
+def _f64(t: torch.Tensor) -> torch.Tensor:
+  if not t.is_cuda or t.dtype != torch.float64:
+    raise ValueError("expected a float64 CUDA tensor")
+  return t.contiguous()
+
+
+def colsq(x: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+  """float64 [d] = alpha * sum_i x[i, j]^2 for x viewed as [-1, d] (aeqb_colsq_f64)."""
+  if not x.is_cuda or x.dtype != torch.float32:
+    raise ValueError("expected a float32 CUDA tensor")
+  x2 = x.contiguous().reshape(-1, x.shape[-1])
+  n, d = x2.shape
+  out = torch.empty(d, dtype=torch.float64, device=x.device)
+  ws = torch.empty(max(_lib.load().aeqb_colsq_workspace_bytes(n, d), 8), dtype=torch.uint8, device=x.device)
+  _lib.call("aeqb_colsq_f64", _ptr(x2), n, d, float(alpha), _ptr(out), _ptr(ws), _stream())
+  return out
+
+
+def oscar_pass(w: torch.Tensor, s: torch.Tensor, group: int, want_a_eff: bool = True):
+  """(group_sq [d / group], a_eff [d] or None): one objective / arg-max pass (aeqb_oscar_pass_f32)."""
+  _check_f32_2d(w)
+  n, d = w.shape
+  s = _f64(s)
+  group_sq = torch.empty(d // group, dtype=torch.float64, device=w.device)
+  a_eff = torch.zeros(d, dtype=torch.float64, device=w.device) if want_a_eff else None
+  ws = torch.empty(max(_lib.load().aeqb_oscar_pass_workspace_bytes(n, d, group), 8), dtype=torch.uint8,
+                   device=w.device)
+  _lib.call("aeqb_oscar_pass_f32", _ptr(w), n, d, group, _ptr(s), _ptr(group_sq), _ptr(a_eff), _ptr(ws),
+            _stream())
+  return group_sq, a_eff
+
+
+def oscar_clip(w: torch.Tensor, s: torch.Tensor, m: torch.Tensor, group: int, qmax: int,
+               mass0: float = 0.0, mass: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """float64 clip bounds, one per group of `group` consecutive values (aeqb_oscar_clip_f32)."""
+  _check_f32_2d(w)
+  n, d = w.shape
+  s, m = _f64(s), _f64(m)
+  bound = torch.empty(n * d // group, dtype=torch.float64, device=w.device)
+  nws = _lib.load().aeqb_oscar_clip_workspace_bytes(n, d, group)
+  ws = torch.empty(nws, dtype=torch.uint8, device=w.device) if nws else None
+  _lib.call("aeqb_oscar_clip_f32", _ptr(w), n, d, group, _ptr(s), _ptr(m),
+            _ptr(None if mass is None else _f64(mass)), float(mass0), int(qmax), _ptr(bound), _ptr(ws),
+            _stream())
+  return bound
+
+
+def oscar_scale(bound: torch.Tensor, qmax: int, blockwise: bool) -> torch.Tensor:
+  """float64 scales from float64 bounds (aeqb_oscar_scale_f64)."""
+  bound = _f64(bound)
+  scale = torch.empty_like(bound)
+  _lib.call("aeqb_oscar_scale_f64", _ptr(bound), bound.numel(), int(qmax), int(blockwise), _ptr(scale),
+            _stream())
+  return scale
+
+
+def oscar_quantize(w: torch.Tensor, s: torch.Tensor, scale: torch.Tensor, group: int, bits: int) -> torch.Tensor:
+  """int8 [n, d] = clip(rint((w * s) / scale[group index])) in float64 (aeqb_oscar_quantize_f32)."""
+  _check_f32_2d(w)
+  n, d = w.shape
+  q = torch.empty((n, d), dtype=torch.int8, device=w.device)
+  _lib.call("aeqb_oscar_quantize_f32", _ptr(w), n, d, group, _ptr(_f64(s)), _ptr(_f64(scale)), bits,
+            _ptr(q), _stream())
+  return q

@@ -24,6 +24,7 @@ from .algorithms.uniform_quantize import hadamard_rotation
 from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
 from .algorithms.uniform_quantize import octav
+from .algorithms.uniform_quantize import oscar
 
 # algorithm key -> (attribute of the reference module holding {op: materialize_fn},
 #                   our get_tensor_quant_params, reference module attr that owns init/calibrate)
@@ -48,6 +49,8 @@ _BINDINGS = {
 _MODULE_SEAMS = {
     "HADAMARD_ROTATION": ("hadamard_rotation", hadamard_rotation.get_tensor_quant_params),
     "DECOMPOSED_HADAMARD_ROTATION": ("hadamard_rotation", hadamard_rotation.get_tensor_quant_params),
+    # oscar._get_or_compute_weight_quant_params calls the module's get_tensor_quant_params (:553)
+    "OSCAR": ("oscar", oscar.get_tensor_quant_params),
 }
 
 

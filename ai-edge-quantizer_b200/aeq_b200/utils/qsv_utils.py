@@ -49,6 +49,30 @@ def gptq_and_moving_average_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV) -> qt
   return out
 
 
+def _oscar_merge_mu2(qsv1: qtyping.QSV, qsv2: qtyping.QSV):
+  """Sample-weighted mean of the per-channel second moments (qsv_utils.py:125-157); O(channels)."""
+  if "mu2" not in qsv1 and "mu2" not in qsv2:
+    return None, 0
+  if "mu2" not in qsv1:
+    return qsv2.get("mu2"), qsv2.get("num_samples", 0)
+  if "mu2" not in qsv2:
+    return qsv1.get("mu2"), qsv1.get("num_samples", 0)
+  n1, n2 = qsv1.get("num_samples", 0), qsv2.get("num_samples", 0)
+  total = n1 + n2
+  if total == 0:
+    return qsv2["mu2"], 0
+  return (qsv1["mu2"] * n1 + qsv2["mu2"] * n2) / total, total
+
+
+def oscar_and_moving_average_update(qsv: qtyping.QSV, new_qsv: qtyping.QSV) -> qtyping.QSV:
+  """EMA on min/max plus the merged mu2 (qsv_utils.py:160-171)."""
+  if not qsv:
+    return new_qsv
+  out = moving_average_update(qsv, new_qsv)
+  out["mu2"], out["num_samples"] = _oscar_merge_mu2(qsv, new_qsv)
+  return out
+
+
 def _merge_hessian(h_old, n_old, h_new, n_new, total):
   """(H_old * n_old + H_new * n_new) / total in float64 on the device (aeqb_hessian_merge_f64).
 

@@ -43,16 +43,50 @@ def _digest() -> str:
   return h.hexdigest()
 
 
+COMPILE_FLAGS = [f for f in FLAGS if f not in ("--shared", "-cudart", "static")]
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _file_digest(src: str) -> str:
+  h = hashlib.sha256()
+  deps = [src] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [
+      os.path.join(HERE, "..", "include", "aeqb200.h")]
+  for p in deps:
+    with open(p, "rb") as f:
+      h.update(p.encode() + b"\0" + f.read())
+  h.update(" ".join(COMPILE_FLAGS).encode())
+  return h.hexdigest()
+
+
+def _compile_one(src: str, force: bool, verbose: bool) -> str:
+  """One translation unit -> build/<name>.o, skipped when source, headers and flags are unchanged."""
+  obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+  stamp = obj + ".stamp"
+  dig = _file_digest(src)
+  if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    return obj
+  cmd = [NVCC, *COMPILE_FLAGS, "-c", "-o", obj, src]
+  if verbose:
+    cmd[1:1] = ["-Xptxas", "-v"]
+    print(" ".join(cmd), file=sys.stderr)
+  subprocess.run(cmd, check=True)
+  with open(stamp, "w") as f:
+    f.write(dig)
+  return obj
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+  """Compiles the translation units in parallel (one nvcc each) and links the shared library."""
+  from concurrent.futures import ThreadPoolExecutor
   dig = _digest()
   if (not force and os.path.exists(OUT) and os.path.exists(STAMP)
       and open(STAMP).read().strip() == dig):
     return OUT
-  cmd = [NVCC, *FLAGS, "-o", OUT, *sources()]
-  if verbose:
-    cmd.insert(1, "-Xptxas")
-    cmd.insert(2, "-v")
-    print(" ".join(cmd), file=sys.stderr)
+  os.makedirs(OBJ_DIR, exist_ok=True)
+  with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+    objs = list(pool.map(lambda s: _compile_one(s, force, verbose), sources()))
+  cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler",
+         "-fPIC,-fvisibility=hidden", "-cudart", "static", "-o", OUT, *objs]
   subprocess.run(cmd, check=True)
   with open(STAMP, "w") as f:
     f.write(dig)

@@ -484,4 +484,78 @@ int aeqb_cast_f32_f16(const float* x, int64_t n, uint16_t* out, void* stream) {
                "aeqb_cast_f32_f16");
 }
 
+size_t aeqb_colsq_workspace_bytes(int64_t n, int64_t d) {
+  return d > 0 ? aeqb::colsq_workspace_bytes(n, d, sm_count()) : 0;
+}
+
+int aeqb_colsq_f64(const float* x, int64_t n, int64_t d, double alpha, double* out, void* ws,
+                   void* stream) {
+  if (n < 0 || d < 0 || d > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)n, (long long)d);
+  if (d == 0) return 0;
+  if (!out || !ws || (n > 0 && !x)) return fail("x / out / ws are NULL");
+  return check(aeqb::launch_colsq(x, n, d, alpha, out, ws, sm_count(), static_cast<cudaStream_t>(stream)),
+               "aeqb_colsq_f64");
+}
+
+static int oscar_group_ok(int64_t n, int64_t d, int64_t g, bool allow_tensor) {
+  if (n <= 0 || d <= 0 || d > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)n, (long long)d);
+  if (g == d || (allow_tensor && g == n * d)) return 0;
+  if ((g == 32 || g == 64 || g == 128 || g == 256) && d % g == 0) return 0;
+  return fail("group length %lld is not the row, a block size dividing %lld, or the tensor",
+              (long long)g, (long long)d);
+}
+
+size_t aeqb_oscar_pass_workspace_bytes(int64_t n, int64_t d, int64_t g) {
+  return (n > 0 && d > 0 && g > 0 && d % g == 0) ? aeqb::oscar_pass_workspace_bytes(n, d, g, sm_count()) : 0;
+}
+
+int aeqb_oscar_pass_f32(const float* w, int64_t n, int64_t d, int64_t g, const double* s,
+                        double* group_sq, double* a_eff, void* ws, void* stream) {
+  if (int rc = oscar_group_ok(n, d, g, false)) return rc;
+  if (!w || !s || !group_sq || !ws) return fail("w / s / group_sq / ws are NULL");
+  return check(aeqb::launch_oscar_pass(w, n, d, g, s, group_sq, a_eff, ws, sm_count(),
+                                       static_cast<cudaStream_t>(stream)),
+               "aeqb_oscar_pass_f32");
+}
+
+size_t aeqb_oscar_clip_workspace_bytes(int64_t n, int64_t d, int64_t g) {
+  return (n > 0 && d > 0) ? aeqb::oscar_clip_workspace_bytes(n, d, g) : 0;
+}
+
+int aeqb_oscar_clip_f32(const float* w, int64_t n, int64_t d, int64_t g, const double* s,
+                        const double* m, const double* mass_dev, double mass0, int qmax,
+                        double* bound, void* ws, void* stream) {
+  if (int rc = oscar_group_ok(n, d, g, true)) return rc;
+  if (!w || !s || !m || !bound) return fail("w / s / m / bound are NULL");
+  if (qmax <= 0) return fail("bad qmax %d", qmax);
+  const bool tensor_form = g == n * d && (n > 1 || d > 16384);
+  if (tensor_form && !ws) return fail("ws is NULL (aeqb_oscar_clip_workspace_bytes)");
+  if (tensor_form && n * d > 0xffffffffLL) return fail("tensor too large for 32-bit sort indices");
+  if (!tensor_form && g == d && d > 16384)
+    return fail("rows longer than 16384 columns are not supported (got %lld)", (long long)d);
+  if (!tensor_form && g != d && g != n * d && !mass_dev) return fail("mass_dev is NULL");
+  return check(aeqb::launch_oscar_clip(w, n, d, g, s, m, mass_dev, mass0, qmax, bound, ws, sm_count(),
+                                       static_cast<cudaStream_t>(stream)),
+               "aeqb_oscar_clip_f32");
+}
+
+int aeqb_oscar_scale_f64(const double* bound, int64_t n, int qmax, int blockwise, double* scale,
+                         void* stream) {
+  if (n < 0 || qmax <= 0) return fail("bad arguments");
+  if (n > 0 && (!bound || !scale)) return fail("bound / scale are NULL");
+  return check(aeqb::launch_oscar_scale(bound, n, qmax, blockwise, scale, static_cast<cudaStream_t>(stream)),
+               "aeqb_oscar_scale_f64");
+}
+
+int aeqb_oscar_quantize_f32(const float* w, int64_t n, int64_t d, int64_t group_len, const double* s,
+                            const double* scale, int bits, int8_t* q, void* stream) {
+  if (n < 0 || d < 0 || d > 0x7fffffff || group_len <= 0) return fail("bad shape");
+  if (!bits_ok(bits)) return fail("num_bits must be 2, 4 or 8, got %d", bits);
+  if (n * d == 0) return 0;
+  if (!w || !s || !scale || !q) return fail("w / s / scale / q are NULL");
+  return check(aeqb::launch_oscar_quantize(w, n, d, group_len, s, scale, bits, q, sm_count(),
+                                           static_cast<cudaStream_t>(stream)),
+               "aeqb_oscar_quantize_f32");
+}
+
 }  // extern "C"

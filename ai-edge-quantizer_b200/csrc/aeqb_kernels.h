@@ -156,6 +156,24 @@ cudaError_t launch_quantize(const float* x, long long n, long long channels, lon
 cudaError_t launch_dequantize(const void* q, int q_bytes, long long n, long long channels,
                               long long inner, const float* scale, const int32_t* zp, int pstride,
                               int wrap8, float* out, int sm_count, cudaStream_t st);
+// oscar.cu
+size_t colsq_workspace_bytes(long long n, long long d, int sm_count);
+cudaError_t launch_colsq(const float* x, long long n, long long d, double alpha, double* out,
+                         void* ws, int sm_count, cudaStream_t st);
+size_t oscar_pass_workspace_bytes(long long n, long long d, long long g, int sm_count);
+cudaError_t launch_oscar_pass(const float* W, long long n, long long d, long long g, const double* s,
+                              double* group_sq, double* a_eff, void* ws, int sm_count,
+                              cudaStream_t st);
+size_t oscar_clip_workspace_bytes(long long n, long long d, long long g);
+cudaError_t launch_oscar_clip(const float* W, long long n, long long d, long long g,
+                              const double* s, const double* m, const double* mass_dev,
+                              double mass0, int qmax, double* bound, void* ws, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_oscar_scale(const double* bound, long long n, int qmax, int blockwise,
+                               double* scale, cudaStream_t st);
+cudaError_t launch_oscar_quantize(const float* W, long long n, long long d, long long glen,
+                                  const double* s, const double* scale, int bits, int8_t* q,
+                                  int sm_count, cudaStream_t st);
 // recovery.cu
 size_t dwr_workspace_bytes(long long n_groups, long long glen);
 cudaError_t launch_dwr_scales(const float* x, long long n_groups, long long glen, float* scale,

@@ -294,6 +294,45 @@ AEQB_API int aeqb_max_abs_diff_f32(const float* a, const float* b, int64_t n, fl
  * float_casting.materialize_fc_conv (algorithms/nonlinear_quantize/float_casting.py:160-162). */
 AEQB_API int aeqb_cast_f32_f16(const float* x, int64_t n, uint16_t* out, void* stream);
 
+/* ---------------------------------------------------------------- OSCAR (float64 like the reference)
+ * out[j] (float64) = alpha * sum_i x[i, j]^2 over a [n, d] fp32 matrix: oscar.calibrate's
+ * mu2 = mean(x*x, axis=0) (algorithms/uniform_quantize/oscar.py:271-277, alpha = 1/n) and
+ * _compute_channel_scales' a_base (:213, alpha = 1).  ws: aeqb_colsq_workspace_bytes(n, d). */
+AEQB_API size_t aeqb_colsq_workspace_bytes(int64_t n, int64_t d);
+AEQB_API int aeqb_colsq_f64(const float* x, int64_t n, int64_t d, double alpha, double* out,
+                            void* ws, void* stream);
+
+/* One pass of oscar._channel_scale_objective (:172-189) and of the a_eff scatter (:223-230) for
+ * channel scales s[d] (float64) and column groups of g (g == d: the whole row):
+ *   group_sq[d / g] = sum_i (max_{j in group} |w_ij| s_j)^2
+ *   a_eff[d] += w[i, j*]^2 at the first arg-max column j* of every (row, group); the caller
+ *   zeroes a_eff; NULL skips it.  ws: aeqb_oscar_pass_workspace_bytes(n, d, g). */
+AEQB_API size_t aeqb_oscar_pass_workspace_bytes(int64_t n, int64_t d, int64_t g);
+AEQB_API int aeqb_oscar_pass_f32(const float* w, int64_t n, int64_t d, int64_t g, const double* s,
+                                 double* group_sq, double* a_eff, void* ws, void* stream);
+
+/* oscar._optimal_group_clip (:62-104) on a = |w * s| with column masses m[d] (float64):
+ * g == d: bound[n] per row; g in {32, 64, 128, 256}: bound[n * d / g] per block;
+ * g == n * d: bound[1] for the whole tensor (masses tiled).  mass_dev: DEVICE array of the
+ * group masses sum(m) + 1e-12 (d / g entries) for the blockwise form; mass0: the same number
+ * for the row / tensor forms (host value).  d <= 16384 for the row form.
+ * ws: aeqb_oscar_clip_workspace_bytes(n, d, g) (non-zero for the tensor form only). */
+AEQB_API size_t aeqb_oscar_clip_workspace_bytes(int64_t n, int64_t d, int64_t g);
+AEQB_API int aeqb_oscar_clip_f32(const float* w, int64_t n, int64_t d, int64_t g, const double* s,
+                                 const double* m, const double* mass_dev, double mass0, int qmax,
+                                 double* bound, void* ws, void* stream);
+
+/* scale[i] (float64) = max(|bound[i]|, 1e-9) / qmax, blockwise != 0: rounded
+ * float32 -> bf16 -> fp16 (tensor_zp_scale_from_min_max on float64 bounds, uqt:492-586). */
+AEQB_API int aeqb_oscar_scale_f64(const double* bound, int64_t n, int qmax, int blockwise,
+                                  double* scale, void* stream);
+
+/* q[i, j] (int8) = clip(rint((w_ij * s_j) / scale[(i * d + j) / group_len])) in float64:
+ * uniform_quantize of the scaled weight (oscar.py:455-457; narrow range for 8 bits). */
+AEQB_API int aeqb_oscar_quantize_f32(const float* w, int64_t n, int64_t d, int64_t group_len,
+                                     const double* s, const double* scale, int bits, int8_t* q,
+                                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

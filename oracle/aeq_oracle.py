@@ -492,6 +492,117 @@ def fake_quantized_weight(rows: int, cols: int, bits: int, block: int = 0, index
 
 
 # --------------------------------------------------------------------------
+# §8(f) row 3: OSCAR (float64 throughout, FULLY_CONNECTED weights [out, in])
+# --------------------------------------------------------------------------
+OSCAR_EPS = 1e-12  # oscar.py:52
+
+
+def oscar_floor(mu2):
+  """Dead-channel guard (oscar.py:56-59)."""
+  mu2 = np.asarray(mu2, np.float64)
+  return np.maximum(mu2, float(np.max(mu2)) * 1e-8 + OSCAR_EPS)
+
+
+def oscar_mu2(x):
+  """calibrate's per-channel second moment (oscar.py:271-277)."""
+  x2 = np.asarray(x, np.float64).reshape(-1, x.shape[-1])
+  return np.mean(x2 * x2, axis=0)
+
+
+def oscar_group_clip(a, m, qmax: int):
+  """Per-row exact minimiser of c^2 M / (12 q^2) + sum_j max(a_j - c, 0)^2 m_j (oscar.py:62-104).
+
+  a: [n, g] magnitudes, m: [g] masses.  Breakpoint scan: with the k+1 largest magnitudes
+  clipped the objective is a parabola in c, minimised in closed form and clamped to its
+  segment; candidate 0 is "no clipping"."""
+  n, g = a.shape
+  order = np.argsort(-a, axis=1)
+  hi = np.take_along_axis(a, order, 1)
+  w = m[order]
+  mass = float(m.sum()) + OSCAR_EPS
+  sm, sam, sa2m = np.cumsum(w, 1), np.cumsum(hi * w, 1), np.cumsum(hi * hi * w, 1)
+  c = 2.0 * sam / (mass / (6.0 * qmax * qmax) + 2.0 * sm)
+  lo = np.concatenate([hi[:, 1:], np.zeros((n, 1))], 1)
+  c = np.clip(c, lo, hi)
+  e = (c ** 2) * (mass / (12.0 * qmax * qmax)) + sa2m - 2.0 * c * sam + (c ** 2) * sm
+  c0 = hi[:, :1]
+  e0 = (c0 ** 2) * (mass / (12.0 * qmax * qmax))
+  cc, ee = np.concatenate([c0, c], 1), np.concatenate([e0, e], 1)
+  return cc[np.arange(n), np.argmin(ee, 1)]
+
+
+def oscar_objective(w, s, mu2, block: int) -> float:
+  """sum over column groups of (sum_i max_j (|w_ij| s_j)^2) * sum_j mu2_j / s_j^2 (oscar.py:172-189)."""
+  m, a = mu2 / (s * s), np.abs(w) * s
+  d = w.shape[1]
+  g = block if (block and d % block == 0) else d
+  total = 0.0
+  for b in range(d // g):
+    mx = a[:, b * g:(b + 1) * g].max(1)
+    total += float((mx * mx).sum()) * float(m[b * g:(b + 1) * g].sum())
+  return total
+
+
+def oscar_channel_scales(w, mu2, block: int = 0, iters: int = 3):
+  """Alternating fixed point for the per-input-channel scales (oscar.py:192-251).
+  Returns None when no candidate beats s = 1."""
+  w = np.asarray(w, np.float64)
+  mu2 = oscar_floor(mu2)
+  mu = np.sqrt(mu2)
+  n, d = w.shape
+  g = block if (block and d % block == 0) else d
+
+  def norm(v):
+    return np.clip(v / np.exp(np.mean(np.log(v))), 1e-4, 1e4)
+
+  a_base = (w * w).sum(0) + OSCAR_EPS
+  identity = oscar_objective(w, np.ones(d), mu2, block)
+  s = norm(np.sqrt(mu / np.sqrt(a_base)))
+  best = (oscar_objective(w, s, mu2, block), s)
+  rows = np.arange(n)
+  for _ in range(iters):
+    a_eff = np.zeros(d)
+    mag = np.abs(w) * s
+    for b in range(d // g):
+      j = b * g + np.argmax(mag[:, b * g:(b + 1) * g], 1)
+      np.add.at(a_eff, j, w[rows, j] ** 2)
+    a_eff = np.maximum(a_eff, 0.25 * a_base)
+    s = norm(np.sqrt(s * norm(np.sqrt(mu / np.sqrt(a_eff)))))
+    loss = oscar_objective(w, s, mu2, block)
+    if loss < best[0]:
+      best = (loss, s)
+  return None if best[0] >= identity else best[1]
+
+
+def oscar_requant(w, mu2, bits: int, block: int = 0, per_channel: bool = True):
+  """oscar.get_tensor_quant_params for a 2-D FC weight (oscar.py:373-458)."""
+  w64 = np.asarray(w, np.float64)
+  n, d = w64.shape
+  s = np.ones(d)
+  if mu2 is not None:
+    got = oscar_channel_scales(w64, np.asarray(mu2, np.float64).ravel(), block)
+    s = got if got is not None else s
+  ws = w64 * s
+  m = oscar_floor(np.ones(d) if mu2 is None else np.asarray(mu2, np.float64).ravel() / (s * s))
+  qmax = 2 ** (bits - 1) - 1
+  a = np.abs(ws)
+  if block:
+    bound = np.stack([oscar_group_clip(a[:, b * block:(b + 1) * block], m[b * block:(b + 1) * block], qmax)
+                      for b in range(d // block)], axis=1)
+  elif per_channel:
+    bound = oscar_group_clip(a, m, qmax).reshape(n, 1)
+  else:
+    bound = oscar_group_clip(a.reshape(1, n * d), np.tile(m, n), qmax).reshape(1, 1)
+  scale = np.maximum(bound, 1e-9) / qmax  # uqt:553-563 on float64 bounds
+  if block:
+    scale = round_scale_bf16_fp16(scale)
+  zp = np.zeros(scale.shape, dtype=qdtype(bits))
+  q = quantize(ws, scale, zp, bits, True, block)
+  return {"scale": scale, "zero_point": zp, "q": q, "bound": bound, "channel_scale": s,
+          "multiplier": (1.0 / s).astype(F32)}
+
+
+# --------------------------------------------------------------------------
 # a13 / a14: bit packing and the serialised blockwise scale
 #            (transformations/transformation_utils.py:293-353,
 #             transformations/quantize_tensor.py:107-147)

@@ -62,7 +62,7 @@ def main():
   for name, fn in (("minmax", gen_minmax), ("octav", gen_octav), ("mse", gen_mse),
                    ("hadamard", gen_hadamard), ("gptq", gen_gptq),
                    ("calibration", gen_calibration), ("pack", gen_pack),
-                   ("histogram", gen_histogram), ("recovery", gen_recovery)):
+                   ("histogram", gen_histogram), ("recovery", gen_recovery), ("oscar", gen_oscar)):
     if not only or name in only:
       fn()
 
@@ -218,6 +218,37 @@ def gen_recovery():
   w[5, 0], w[5, 1], w[5, 2] = 70000.0, -65520.0, 6e-8  # overflow to inf, the rounding boundary, a subnormal
   out["cast_in"], out["cast_out"] = w, w.astype(np.float16)
   save("recovery", **out)
+
+
+def oscar_mu2(d, seed):
+  rng = np.random.default_rng(seed)
+  mu2 = rng.standard_normal(d) ** 2 * 0.5 + 0.01
+  mu2[::17] *= 40.0
+  mu2[3] = 0.0
+  return mu2
+
+
+def gen_oscar():
+  """OSCAR end to end (channel scales, clip bounds, scale, integers) + calibrate's mu2."""
+  OSC = refshim.ref("algorithms.uniform_quantize.oscar")
+  out, cases = {}, []
+  specs = [(4, 0, (16, 512), True), (8, 0, (16, 512), True), (4, 32, (16, 512), True),
+           (4, 128, (16, 512), False), (4, -1, (64, 512), True), (8, 0, (6, 11008), False),
+           (4, 0, (5, 100), True)]
+  for i, (bits, gk, shape, with_mu2) in enumerate(specs):
+    w = weight(shape[0], shape[1], 40 + i, special=False)
+    w[1, :] = 0.0
+    mu2 = oscar_mu2(shape[1], i) if with_mu2 else None
+    r = run(OSC, w, cfg(bits, True, gk), qsv=({"mu2": mu2} if with_mu2 else None))
+    out[f"w{i}"], out[f"scale{i}"], out[f"q{i}"] = w, r.scale, r.quantized_data
+    out[f"mult{i}"] = r.custom_algorithm_param["multiplier"]
+    if with_mu2:
+      out[f"mu2_{i}"] = mu2
+    cases.append((bits, gk, int(with_mu2)))
+  out["cases"] = np.array(cases)
+  x = O.synthetic_activation((3, 70, 96), 8)
+  out["act"], out["act_mu2"] = x, np.mean(np.asarray(x, np.float64).reshape(-1, 96) ** 2, axis=0)
+  save("oscar", **out)
 
 
 def gen_pack():

@@ -104,6 +104,34 @@ def test_module_registry_has_hot_path_ops():
     assert m.func is common_utils.materialize_weight_op
 
 
+def test_every_algorithm_key_is_registered():
+  """All AlgorithmName keys of the reference (algorithm_manager.py:65-75) resolve here;
+  `no_quantize` is a marker the callers test for, not a registered algorithm."""
+  for alg in am.AlgorithmName:
+    if alg == am.AlgorithmName.NO_QUANTIZE:
+      continue
+    assert am.is_algorithm_registered(alg), alg
+    assert Op.FULLY_CONNECTED in am.get_supported_ops(alg)
+  assert am.get_supported_ops(am.AlgorithmName.OSCAR) == [Op.FULLY_CONNECTED]
+  assert am.get_update_qsv_func(am.AlgorithmName.OSCAR, Op.FULLY_CONNECTED) is (
+      qsv_utils.oscar_and_moving_average_update)
+  assert Op.DEPTHWISE_CONV_2D in am.get_supported_ops(am.AlgorithmName.FLOAT_CASTING)
+
+
+def test_oscar_qsv_merge_matches_reference():
+  from oracle import refshim
+  a = {"min": np.float32([[-1.0]]), "max": np.float32([[2.0]]), "mu2": np.array([1.0, 4.0]), "num_samples": 3}
+  b = {"min": np.float32([[-3.0]]), "max": np.float32([[1.0]]), "mu2": np.array([2.0, 0.5]), "num_samples": 1}
+  got = qsv_utils.oscar_and_moving_average_update(a, b)
+  np.testing.assert_array_equal(got["mu2"], (a["mu2"] * 3 + b["mu2"] * 1) / 4)
+  assert got["num_samples"] == 4 and qsv_utils.oscar_and_moving_average_update({}, b) is b
+  if refshim.available():
+    want = refshim.ref("utils.qsv_utils").oscar_and_moving_average_update(a, b)
+    for k in ("min", "max", "mu2"):
+      np.testing.assert_array_equal(got[k], want[k])
+    assert got["num_samples"] == want["num_samples"]
+
+
 def test_blockwise_config_rules():
   blk = qtyping.TensorQuantizationConfig(4, True, G.BLOCKWISE_32)
   am.check_op_quantization_config("min_max_uniform_quantize", Op.FULLY_CONNECTED,
@@ -204,7 +232,8 @@ def test_plugin_installs_into_reference_registry():
   ref_had = ram.hadamard_rotation.get_tensor_quant_params
   bound = plugin.install(ram)
   try:
-    assert {"min_max_uniform_quantize", "OCTAV", "MSE", "HADAMARD_ROTATION"} <= set(bound)
+    assert {"min_max_uniform_quantize", "OCTAV", "MSE", "HADAMARD_ROTATION", "GPTQ", "OSCAR",
+            "dequantized_weight_recovery"} <= set(bound)
     for key in ("min_max_uniform_quantize", "OCTAV", "MSE"):
       f = ram.get_quantization_func(key, rq.TFLOperationName.FULLY_CONNECTED,
                                     rq.QuantizeMode.MATERIALIZE)

@@ -284,3 +284,17 @@ def test_recovery_fixtures_bit_exact():
     np.testing.assert_array_equal(o["q"], z[f"q{i}"])
   with np.errstate(all="ignore"):
     np.testing.assert_array_equal(O.float_cast(z["cast_in"]).view(np.uint16), z["cast_out"].view(np.uint16))
+
+
+def test_oscar_fixtures_bit_exact():
+  """OSCAR fixtures (tests/golden/oscar.npz): the oracle restates the reference's float64
+  NumPy expressions, so everything is bit-identical."""
+  z = np.load(os.path.join(GOLD, "oscar.npz"))
+  for i, (bits, gk, with_mu2) in enumerate(z["cases"]):
+    mu2 = z[f"mu2_{i}"] if with_mu2 else None
+    with np.errstate(all="ignore"):
+      o = O.oscar_requant(z[f"w{i}"], mu2, int(bits), block=max(int(gk), 0), per_channel=(gk == 0))
+    np.testing.assert_array_equal(o["scale"], z[f"scale{i}"])
+    np.testing.assert_array_equal(o["q"], z[f"q{i}"])
+    np.testing.assert_array_equal(o["multiplier"], z[f"mult{i}"])
+  np.testing.assert_array_equal(O.oscar_mu2(z["act"]), z["act_mu2"])

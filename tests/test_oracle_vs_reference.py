@@ -155,3 +155,40 @@ def test_dequantized_weight_recovery_literal(R):
   np.testing.assert_array_equal(O.dwr_requant(deq, 8, per_channel=False)["scale"], sc)
   zp, sc = dwr.get_zp_scale_from_dequantized_symmetric_weights(deq, 0)
   np.testing.assert_array_equal(O.dwr_group_scales(deq).reshape(2, 1), sc)
+
+
+# ---- §8(f) row 3: OSCAR ------------------------------------------------------------------
+def _mu2(d, seed):
+  rng = np.random.default_rng(seed)
+  mu2 = rng.standard_normal(d) ** 2 * 0.5 + 0.01
+  mu2[::17] *= 40.0   # a few hot input channels: this is what makes scaling pay
+  mu2[3] = 0.0        # a dead channel (floored)
+  return mu2
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("gk", [0, -1, 32, 128])
+@pytest.mark.parametrize("with_mu2", [True, False])
+def test_oscar(R, bits, gk, with_mu2):
+  osc = refshim.ref("algorithms.uniform_quantize.oscar")
+  w = O.synthetic_weight(24, 256, bits + gk % 5)
+  w[1, :] = 0.0
+  mu2 = _mu2(256, bits) if with_mu2 else None
+  r = _run(R, osc, w, bits, True, gk, qsv=({"mu2": mu2} if with_mu2 else None))
+  with np.errstate(all="ignore"):
+    o = O.oscar_requant(w, mu2, bits, block=max(gk, 0), per_channel=(gk == 0))
+  np.testing.assert_array_equal(o["scale"], r.scale)
+  assert o["scale"].dtype == r.scale.dtype and o["scale"].shape == r.scale.shape
+  np.testing.assert_array_equal(o["zero_point"], r.zero_point)
+  assert o["zero_point"].dtype == r.zero_point.dtype
+  np.testing.assert_array_equal(o["q"], r.quantized_data)
+  np.testing.assert_array_equal(o["multiplier"], r.custom_algorithm_param["multiplier"])
+  if with_mu2:
+    assert not np.all(o["channel_scale"] == 1.0), "the fixture must exercise channel scaling"
+
+
+def test_oscar_mu2_and_merge(R):
+  osc = refshim.ref("algorithms.uniform_quantize.oscar")
+  x = O.synthetic_activation((3, 50, 64), 4)
+  np.testing.assert_array_equal(O.oscar_mu2(x), np.mean(np.asarray(x, np.float64).reshape(-1, 64) ** 2, axis=0))
+  np.testing.assert_array_equal(O.oscar_floor(_mu2(64, 1)), osc._floor_positive(_mu2(64, 1)))
