@@ -115,8 +115,18 @@ def materialize_weight_op(get_tensor_quant_params_fn, op_info: qtyping.OpInfo,
       data = tfl_flatbuffer_utils.get_tensor_data(tensor, graph_info.buffers)
       constant = data is not None
       tcfg = cfg.activation_tensor_config
-      if constant and op_info.op_name in _DRQ_OR_WEIGHT_ONLY_OPS:
+      # Only the weight operand (input 1 of FC / CONV / TRANSPOSE_CONV / EMBEDDING_LOOKUP) takes
+      # the weight config; a constant bias stays float unless activations are quantised too
+      # (common_quantize.materialize_fc_conv: bias is handled by the SRQ path only).
+      if constant and inbound and pos == 1 and op_info.op_name in _DRQ_OR_WEIGHT_ONLY_OPS:
         tcfg = cfg.weight_tensor_config
+      elif constant:
+        if tcfg is not None:
+          raise NotImplementedError(
+              f"static-range quantisation of the constant '{name}' (bias: int32 with scale ="
+              " input scale x weight scale) is part of the reference's materialize_fc_conv; use"
+              " aeq_b200.plugin.install with the reference for SRQ recipes")
+        tcfg = None
       skip = (inbound and pos in inputs_to_ignore) or tcfg is None or (
           constant and (data.dtype != "float32" or data.size < cfg.min_weight_elements))
       params, transformations = None, [_QT.NO_QUANTIZE]

@@ -10,8 +10,36 @@ from __future__ import annotations
 import numpy as np
 
 from .. import qtyping
+from . import tfl_model
 
 _Op = qtyping.TFLOperationName
+
+# Model I/O (reference :118-160 goes through ai_edge_litert's flatbuffer_utils; here the TFL3
+# wire format is read and written by aeq_b200.utils.tfl_model / flatbuffer_lite).
+read_model = tfl_model.read_model
+read_model_from_bytes = tfl_model.read_model_from_bytes
+write_model = tfl_model.write_model
+write_model_to_bytes = tfl_model.write_model_to_bytes
+
+# Builtin operator code -> op name, for the ops whose constants reach the hot path
+# (reference TFL_OP_CODE_TO_NAME, :32-92, restricted to the weight-carrying ops).
+TFL_OP_CODE_TO_NAME = qtyping.FrozenParams({
+    tfl_model.BuiltinOperator.FULLY_CONNECTED: _Op.FULLY_CONNECTED,
+    tfl_model.BuiltinOperator.CONV_2D: _Op.CONV_2D,
+    tfl_model.BuiltinOperator.DEPTHWISE_CONV_2D: _Op.DEPTHWISE_CONV_2D,
+    tfl_model.BuiltinOperator.EMBEDDING_LOOKUP: _Op.EMBEDDING_LOOKUP,
+    tfl_model.BuiltinOperator.TRANSPOSE_CONV: _Op.CONV_2D_TRANSPOSE,
+    tfl_model.BuiltinOperator.BATCH_MATMUL: _Op.BATCH_MATMUL,
+})
+
+
+def get_op_scope(op, subgraph_tensors) -> str:
+  """Output tensor names joined with ';' — what recipe regexes match (reference :371-415)."""
+  def names(ids):
+    return [n for n in (get_tensor_name(subgraph_tensors[i]) for i in ids if i != -1) if n]
+  found = names(op.outputs) or names(op.inputs)
+  return ";".join(found) + (";" if found else "")
+
 
 # Per-channel quantised dimension of the weight (TFLite quantisation spec).
 TFL_OP_TO_WEIGHT_QUANTIZED_DIM = qtyping.FrozenParams({
