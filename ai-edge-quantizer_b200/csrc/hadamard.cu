@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256)
     hadamard_rows_reg(const float* __restrict__ x, long long rows, int cols, int n, float norm,
                       float* __restrict__ out) {
   extern __shared__ __align__(16) float s_row[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
   const int ngroups = cols >> 8;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {

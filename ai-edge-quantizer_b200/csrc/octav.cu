@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(THREADS)
   __shared__ float s_sum[2][NW];
   __shared__ float s_cnt[2][NW];
   __shared__ int s_zero[NW];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nvec = cols >> 2;
   unsigned my_mask = 0;
   float4 nxt[NV];
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256)
   __shared__ unsigned s_mask;
   if (threadIdx.x == 0) s_mask = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   float* t = s_t[warp];
   const long long nblk = n / BLOCK;
   const long long nwt = (n + 1023) / 1024;  // warp tiles

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kMmThreads)
                           int use_hi, float* __restrict__ ws) {
   __shared__ TensorAcc s_w[kMmThreads / 32];
   __shared__ int s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   float* slots = ws + 8 + static_cast<size_t>(blockIdx.x) * b.n_jobs * 4;
   for (int j = tid; j < b.n_jobs; j += kMmThreads) {
     float* s = slots + j * 4;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
   constexpr int LPB = BLOCK / 8;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   const int lane = tid & 31;
   const long long n_tiles = b.n_tiles;
 
