@@ -489,6 +489,18 @@ static int min_stream_class() {
   return v;
 }
 
+// Whole rows per tile of a class (stage bytes / row bytes, capped).
+static int class_rows_per_tile(int cols, int klass) {
+  const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : 65536);
+  long long rpt = stage / (static_cast<long long>(cols) * 4);
+  if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
+  return static_cast<int>(rpt);
+}
+
+// Every tile costs its CTA one pass-1 -> barrier -> pass-2 round trip whatever it holds, so the
+// class is the one that moves the most bytes per round trip and SM: (CTAs per SM) x (rows per
+// tile) x (row bytes); ties go to the smaller class (more independent pipelines).  A 20 KiB row
+// fills 62 % of a class-2 tile (2 CTAs x 20 KiB) but 94 % of a class-3 tile (3 rows, 60 KiB).
 int rows_job_class(const RowsJob& j, int bits) {
   const long long row_bytes = static_cast<long long>(j.cols) * 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
@@ -496,17 +508,20 @@ int rows_job_class(const RowsJob& j, int bits) {
                        (!j.packed || reinterpret_cast<uintptr_t>(j.packed) % 4 == 0);
   (void)bits;
   if (!aligned || j.cols % kChunk != 0 || row_bytes > 65536) return 0;
-  int k = row_bytes <= 16384 ? 1 : (row_bytes <= 32768 ? 2 : 3);
-  if (k < min_stream_class()) k = min_stream_class();
-  return k;
+  int best = 0;
+  long long best_bytes = -1;
+  for (int k = min_stream_class() < 1 ? 1 : min_stream_class(); k <= 3; ++k) {
+    const int ctas = k == 1 ? 4 : (k == 2 ? 2 : 1);
+    const long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
+    if (bytes > best_bytes) {
+      best_bytes = bytes;
+      best = k;
+    }
+  }
+  return best;
 }
 
-int rows_job_rows_per_tile(const RowsJob& j, int klass) {
-  const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : 65536);
-  long long rpt = stage / (static_cast<long long>(j.cols) * 4);
-  if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
-  return static_cast<int>(rpt);
-}
+int rows_job_rows_per_tile(const RowsJob& j, int klass) { return class_rows_per_tile(j.cols, klass); }
 
 cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count,
                                        cudaStream_t st) {

@@ -15,7 +15,8 @@ def main():
   peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
   dev = torch.device("cuda:0")
   shapes = [(4096, 4096), (11008, 4096), (4096, 11008), (2048, 2048), (256, 2048), (16384, 2048),
-            (2048, 16384), (4096, 8192), (4096, 14336)]
+            (2048, 16384), (4096, 8192), (4096, 14336), (4096, 5120), (4096, 6144), (4096, 3584),
+            (4096, 2560), (8192, 1536), (4096, 13824)]
   for r, c in shapes:
     n = max(2, int(2e9 // (r * c * 4)))  # ~2 GB per stack: far beyond L2
     ws = [torch.randn(r, c, device=dev) * 0.02 for _ in range(n)]
