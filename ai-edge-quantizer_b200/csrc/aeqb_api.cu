@@ -71,7 +71,7 @@ struct RowsOpts { int bits, symmetric; };
 // class (one persistent launch each), the rest go through the generic kernel.
 int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who) {
   const int sms = sm_count();
-  for (int klass = 1; klass <= 3; ++klass) {
+  for (int klass = 1; klass <= 4; ++klass) {
     aeqb::RowsBatch b{};
     b.bits = o.bits; b.symmetric = o.symmetric;
     auto flush = [&]() -> int {

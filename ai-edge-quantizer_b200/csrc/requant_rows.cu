@@ -29,10 +29,8 @@ namespace aeqb {
 
 namespace {
 
-constexpr int kStages = 3;
 constexpr int kMaxRowsPerTile = 64;
 constexpr int kChunk = 128;   // floats per warp chunk
-constexpr int kMaxChunksPerWarp = 8;
 
 struct RowAcc {  // merged across warps with shared-memory atomics
   unsigned amax_bits;
@@ -129,11 +127,11 @@ __device__ __forceinline__ float div_row(float x, const RowQ& rq) {
 // Pass 2 of a tile whose rows are all symmetric / unclipped / inside the divide window.
 // Branch-free; partial tiles (row length not a multiple of NW chunks, tensor tails) compute their
 // unused chunk slots on zeros and predicate only the store.
-template <bool FULL, int NW>
-__device__ __forceinline__ void tight_pass2(const float4 (&v)[kMaxChunksPerWarp], const float2* by_slots,
+template <bool FULL, int NW, int SLOTS>
+__device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const float2* by_slots,
                                             int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks) {
 #pragma unroll
-  for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+  for (int j = 0; j < SLOTS; ++j) {
     const bool valid = FULL || warp + j * NW < nchunks;  // partial tiles: only the store is predicated
     const float2 by = by_slots[j];
     // The hoisted exact divide on the packed-fp32 pipe: two elements per FMUL2 / FFMA2
@@ -155,16 +153,20 @@ __device__ __forceinline__ void tight_pass2(const float4 (&v)[kMaxChunksPerWarp]
 }
 
 // ------------------------------------------------------------------ TMA tile stream
-template <int STAGE_BYTES, int NW>
+// SLOTS = chunk slots (128 floats each) per consumer warp and tile, STAGES = depth of the ring.
+// Classes 1-3 use 8 slots and 3 stages; the wide class (4) uses 12 slots and 2 stages of 96 KiB so
+// that one round trip of a CTA moves up to 96 KiB (two 44 KiB rows, four 24 KiB rows).
+template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1)))
     requant_rows_stream(const __grid_constant__ RowsBatch b) {
-  static_assert(STAGE_BYTES / (kChunk * 4) == NW * kMaxChunksPerWarp, "chunks per warp");
+  static_assert(STAGE_BYTES / (kChunk * 4) == NW * SLOTS, "chunks per warp");
+  static_assert(SLOTS <= 32, "one finalising lane per chunk slot");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ StageDesc desc[kStages];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ StageDesc desc[STAGES];
   __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
-  __shared__ float2 s_by[NW][kMaxChunksPerWarp];  // per-warp (scale, reciprocal) of each chunk slot
+  __shared__ float2 s_by[NW][SLOTS];  // per-warp (scale, reciprocal) of each chunk slot
 
   const int tid = threadIdx.x;
   // Broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the per-chunk
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
   const long long n_tiles = b.n_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], NW);
     }
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         mbar_arrive_expect_tx(&full_bar[s], bytes);  // release: desc visible to waiters
         bulk_g2s(smem_raw + static_cast<size_t>(s) * STAGE_BYTES, job.x + row0 * job.cols, bytes,
                  &full_bar[s]);
-        if (++s == kStages) { s = 0; ++round; }
+        if (++s == STAGES) { s = 0; ++round; }
       }
     }
     return;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
   int s = -1, buf = -1;
   uint32_t ph = 1;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    if (++s == kStages) s = 0;
+    if (++s == STAGES) s = 0;
     if (s == 0) ph ^= 1;
     if (++buf == 3) buf = 0;
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * STAGE_BYTES);
@@ -239,16 +241,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
     // atomic per chunk merges the row statistics (no row-change bookkeeping).
     const unsigned magic = job.cpr_magic;  // row of chunk c = (c * magic) >> 20
-    const bool full_tile = nchunks == NW * kMaxChunksPerWarp;
+    const bool full_tile = nchunks == NW * SLOTS;
     const bool plain = abs_scan && !given;
-    float4 v[kMaxChunksPerWarp];
+    float4 v[SLOTS];
     if (plain && full_tile) {  // branch-free common case
       // (Measured SLOWER on B200, 0.85-0.91 vs 0.92 of peak: folding the per-chunk atomics into
       //  one divergent region per tile; folding the chunks of a row in registers before one
       //  REDUX + atomic per row; sleeping between mbarrier polls.  The pass-1 -> barrier -> pass-2
       //  critical path wants short independent chains, not fewer instructions.)
 #pragma unroll
-      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+      for (int j = 0; j < SLOTS; ++j) {
         const int c = warp + j * NW;
         v[j] = t4[c * 32 + lane];
         const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       // every REDUX behind divergence-protected branches: 98 executed instructions per chunk
       // on 11008-wide rows, a quarter of them ISETP / BRA / BSSY / BSYNC.
 #pragma unroll
-      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+      for (int j = 0; j < SLOTS; ++j) {
         const int c = warp + j * NW;
         const bool valid = c < nchunks;
         v[j] = valid ? t4[c * 32 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       }
     } else
 #pragma unroll
-    for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+    for (int j = 0; j < SLOTS; ++j) {
       const int c = warp + j * NW;
       if (c < nchunks) {
         v[j] = t4[c * 32 + lane];
@@ -303,8 +305,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     int8_t* const qp = job.q ? job.q + row0 * cols : nullptr;
     uint8_t* const pp = job.packed ? job.packed + ((row0 * cols * bits) >> 3) : nullptr;
     // Lane l < 8 will finalise the row of this warp's l-th chunk: it needs the job.
-    const int my_c = warp + (lane & 7) * NW;
-    const bool my_valid = lane < kMaxChunksPerWarp && my_c < nchunks;
+    const int my_c = warp + (lane < SLOTS ? lane : 0) * NW;
+    const bool my_valid = lane < SLOTS && my_c < nchunks;
     RowsJob jcopy;
     if (my_valid) jcopy = job;
     __syncwarp();
@@ -344,20 +346,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     if (tid < kMaxRowsPerTile) acc_reset(s_acc[buf == 0 ? 2 : buf - 1][tid]);
 
     // ---- pass 2: quantise from registers + store
-    const bool all_fast = __all_sync(0xffffffffu, lane >= kMaxChunksPerWarp || mine.mode == kFastSym);
+    const bool all_fast = __all_sync(0xffffffffu, lane >= SLOTS || mine.mode == kFastSym);
     if (all_fast && !(pp && bits != 4)) {
       // Tight path: every row of the tile is symmetric / unclipped / in the divide
       // window.  (scale, reciprocal) per chunk slot via one broadcast LDS.64.
-      if (lane < kMaxChunksPerWarp) s_by[warp][lane] = make_float2(mine.b, mine.y);
+      if (lane < SLOTS) s_by[warp][lane] = make_float2(mine.b, mine.y);
       __syncwarp();
       int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
       uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
-      if (full_tile) tight_pass2<true, NW>(v, s_by[warp], ql, pl, lane, warp, nchunks);
-      else tight_pass2<false, NW>(v, s_by[warp], ql, pl, lane, warp, nchunks);
+      if (full_tile) tight_pass2<true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks);
+      else tight_pass2<false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks);
       __syncwarp();  // s_by[warp] is rewritten next tile
     } else {
 #pragma unroll
-      for (int j = 0; j < kMaxChunksPerWarp; ++j) {
+      for (int j = 0; j < SLOTS; ++j) {
         const int c = warp + j * NW;
         RowQ rq;
         rq.b = __shfl_sync(0xffffffffu, mine.b, j);
@@ -461,10 +463,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int STAGE_BYTES, int NW>
+template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
 cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
-  auto kern = requant_rows_stream<STAGE_BYTES, NW>;
-  const int smem = kStages * STAGE_BYTES;
+  auto kern = requant_rows_stream<STAGE_BYTES, NW, SLOTS, STAGES>;
+  const int smem = STAGES * STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -484,6 +486,7 @@ cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cud
 //   1: rows <= 16 KiB, 4 consumer warps, 3 x 16 KiB stages, 4 CTAs / SM
 //   2: rows <= 32 KiB, 8 consumer warps, 3 x 32 KiB stages, 2 CTAs / SM
 //   3: rows <= 64 KiB, 16 consumer warps, 3 x 64 KiB stages, 1 CTA / SM
+//   4: rows <= 96 KiB, 16 consumer warps x 12 chunk slots, 2 x 96 KiB stages, 1 CTA / SM
 static int min_stream_class() {
   static const int v = getenv("AEQB_ROWS_MIN_CLASS") ? atoi(getenv("AEQB_ROWS_MIN_CLASS")) : 1;
   return v;
@@ -491,7 +494,7 @@ static int min_stream_class() {
 
 // Whole rows per tile of a class (stage bytes / row bytes, capped).
 static int class_rows_per_tile(int cols, int klass) {
-  const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : 65536);
+  const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : (klass == 3 ? 65536 : 98304));
   long long rpt = stage / (static_cast<long long>(cols) * 4);
   if (rpt > kMaxRowsPerTile) rpt = kMaxRowsPerTile;
   return static_cast<int>(rpt);
@@ -499,20 +502,23 @@ static int class_rows_per_tile(int cols, int klass) {
 
 // Every tile costs its CTA one pass-1 -> barrier -> pass-2 round trip whatever it holds, so the
 // class is the one that moves the most bytes per round trip and SM: (CTAs per SM) x (rows per
-// tile) x (row bytes); ties go to the smaller class (more independent pipelines).  A 20 KiB row
-// fills 62 % of a class-2 tile (2 CTAs x 20 KiB) but 94 % of a class-3 tile (3 rows, 60 KiB).
+// tile) x (row bytes), counted up to 64 KiB (beyond that HBM is the limit); ties go to the
+// smaller class (more independent pipelines).  Measured: a 20 KiB row reaches 0.62 of the HBM
+// peak in class 2 (2 CTAs x 20 KiB) and 0.96 in class 4 (4 rows, 80 KiB); a 44 KiB row 0.68 in
+// class 3 (one row per tile) and 1.02 in class 4 (two rows).
 int rows_job_class(const RowsJob& j, int bits) {
   const long long row_bytes = static_cast<long long>(j.cols) * 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
                        (!j.q || reinterpret_cast<uintptr_t>(j.q) % 4 == 0) &&
                        (!j.packed || reinterpret_cast<uintptr_t>(j.packed) % 4 == 0);
   (void)bits;
-  if (!aligned || j.cols % kChunk != 0 || row_bytes > 65536) return 0;
+  if (!aligned || j.cols % kChunk != 0 || row_bytes > 98304) return 0;
   int best = 0;
   long long best_bytes = -1;
-  for (int k = min_stream_class() < 1 ? 1 : min_stream_class(); k <= 3; ++k) {
+  for (int k = min_stream_class() < 1 ? 1 : min_stream_class(); k <= 4; ++k) {
     const int ctas = k == 1 ? 4 : (k == 2 ? 2 : 1);
-    const long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
+    long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
+    if (bytes > 65536) bytes = 65536;  // 64 KiB per round trip already saturates HBM (measured)
     if (bytes > best_bytes) {
       best_bytes = bytes;
       best = k;
@@ -526,9 +532,10 @@ int rows_job_rows_per_tile(const RowsJob& j, int klass) { return class_rows_per_
 cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count,
                                        cudaStream_t st) {
   if (b.n_tiles <= 0) return cudaSuccess;
-  if (klass == 1) return launch_stream<16384, 4>(b, sm_count, 4, st);
-  if (klass == 2) return launch_stream<32768, 8>(b, sm_count, 2, st);
-  return launch_stream<65536, 16>(b, sm_count, 1, st);
+  if (klass == 1) return launch_stream<16384, 4, 8, 3>(b, sm_count, 4, st);
+  if (klass == 2) return launch_stream<32768, 8, 8, 3>(b, sm_count, 2, st);
+  if (klass == 3) return launch_stream<65536, 16, 8, 3>(b, sm_count, 1, st);
+  return launch_stream<98304, 16, 12, 2>(b, sm_count, 1, st);
 }
 
 cudaError_t launch_requant_rows_generic(const RowsJob& j, int bits, int symmetric,
