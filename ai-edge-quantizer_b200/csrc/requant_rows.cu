@@ -518,7 +518,10 @@ int rows_job_class(const RowsJob& j, int bits) {
   for (int k = min_stream_class() < 1 ? 1 : min_stream_class(); k <= 4; ++k) {
     const int ctas = k == 1 ? 4 : (k == 2 ? 2 : 1);
     long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
-    if (bytes > 65536) bytes = 65536;  // 64 KiB per round trip already saturates HBM (measured)
+    // 64 KiB per round trip saturates HBM with int8 output; the packed INT4 / INT2 pass 2 is
+    // longer, so its round trip wants 96 KiB (4096-wide rows: 0.84 of peak in class 1, 0.95 in 4).
+    const long long cap = (j.packed && !j.q) ? 98304 : 65536;
+    if (bytes > cap) bytes = cap;
     if (bytes > best_bytes) {
       best_bytes = bytes;
       best = k;
