@@ -38,7 +38,7 @@ def _digest() -> str:
       if f.endswith((".h", ".cuh"))) + [
           os.path.join(HERE, "..", "include", "aeqb200.h"), __file__]:
     with open(p, "rb") as f:
-      h.update(p.encode() + b"\0" + f.read())
+      h.update(os.path.basename(p).encode() + b"\0" + f.read())  # location-independent
   h.update(" ".join(FLAGS).encode())
   return h.hexdigest()
 
@@ -53,7 +53,7 @@ def _file_digest(src: str) -> str:
       os.path.join(HERE, "..", "include", "aeqb200.h")]
   for p in deps:
     with open(p, "rb") as f:
-      h.update(p.encode() + b"\0" + f.read())
+      h.update(os.path.basename(p).encode() + b"\0" + f.read())  # location-independent
   h.update(" ".join(COMPILE_FLAGS).encode())
   return h.hexdigest()
 

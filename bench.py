@@ -292,6 +292,16 @@ def extra_modes(dev, ws, peak, steps):
                                "batches": T, "bytes_per_element": 4.0,
                                "roofline_frac": n_bytes / ms / 1e6 / peak}
 
+  # the same batches, eight per launch (aeqb_minmax_tensors_f32): min / max of a batch do not depend
+  # on other batches, only the EMA that consumes them is sequential (and O(1) per batch on the host)
+  def calib8():
+    for i in range(0, len(acts), 8):
+      device.minmax_tensors(acts[i:i + 8], -3e38, 3e38)
+  ms = timeit(calib8, reps)
+  out["calibration_minmax_8_per_launch"] = {
+      "value": n_bytes / ms / 1e6, "unit": "activation GB/s", "ms_per_step": ms, "batches": T,
+      "bytes_per_element": 4.0, "roofline_frac": n_bytes / ms / 1e6 / peak}
+
   # GPTQ on one [4096, 4096] layer: Hessian from 8192 tokens, damped inverse, OBS loop
   x = torch.randn(8, 1024, COLS, device=dev)
   ms_h = timeit(lambda: device.xtx(x, 2.0 / 8), 3)
