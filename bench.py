@@ -379,6 +379,67 @@ def config_sets(dev, peak, reps):
         "value": n_bytes / ms / 1e6, "ms_per_step": ms, "tensors": len(ws), "fp32_bytes": n_bytes,
         "bytes_per_weight": bpw, "roofline_frac": (n_bytes / 4) * bpw / ms / 1e6 / peak}
     del st
+  del ws
+
+  # ---- configs[4], one Llama-7B decoder layer: Hadamard-rotated INT4 and GPTQ INT4 over its seven
+  # FC weights.  GPTQ needs four Hessians (q/k/v share their input, gate/up too): X^T X over
+  # `tok` tokens each, the damped inverse, then the OBS loop per weight.
+  def gcd_pow2(n):
+    return n & -n
+
+  layer = make(llama, 1)
+  rot = [torch.empty_like(w) for w in layer]
+
+  def hadamard_layer():
+    for w, r in zip(layer, rot):
+      device.hadamard_rows(w, min(gcd_pow2(w.shape[1]), 4096), out=r)
+      c = device.octav_clip_rows(r, 4)
+      device.requant_rows(r, 4, True, clip=c)
+  ms = timeit(hadamard_layer)
+  lbytes = sum(w.numel() for w in layer) * 4
+  out["cfg5_llama7b_layer_hadamard_octav_int4"] = {
+      "value": lbytes / ms / 1e6, "ms_per_layer": ms, "tensors": len(layer), "fp32_bytes": lbytes,
+      "bytes_per_weight": 17.0, "roofline_frac": (lbytes / 4) * 17.0 / ms / 1e6 / peak}
+  del rot
+
+  tok = 16384
+  t0 = torch.cuda.Event(enable_timing=True)
+  t1 = torch.cuda.Event(enable_timing=True)
+  parts = {"hessian": 0.0, "inverse": 0.0, "obs_loop": 0.0}
+  g = torch.Generator(device=dev).manual_seed(99)
+
+  def timed(fn):
+    t0.record()
+    r = fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return r, t0.elapsed_time(t1)
+
+  for rep in range(2):  # second pass is the measurement
+    for key in parts:
+      parts[key] = 0.0
+    hinv = {}
+    for name, k in (("attn_in", 4096), ("attn_out", 4096), ("mlp_in", 4096), ("mlp_mid", 11008)):
+      x = torch.randn(tok, k, device=dev, generator=g)
+      h, ms_h = timed(lambda: device.xtx(x, 2.0 / 8))
+      del x
+      hi, ms_i = timed(lambda: device.hessian_inverse(h, 0.01))
+      del h
+      hinv[name] = hi
+      parts["hessian"] += ms_h
+      parts["inverse"] += ms_i
+    feeds = ["attn_in"] * 3 + ["attn_out"] + ["mlp_in"] * 2 + ["mlp_mid"]
+    for w, feed in zip(layer, feeds):
+      sc = w.abs().amax(dim=1) / 7.0
+      _, ms_q = timed(lambda: device.gptq_quantize(w, hinv[feed], sc, None, 0, 4, True))
+      parts["obs_loop"] += ms_q
+    del hinv
+  total = sum(parts.values())
+  out["cfg5_llama7b_layer_gptq_int4"] = {
+      "value": lbytes / total / 1e6, "ms_per_layer": total, "ms_hessian_4x": parts["hessian"],
+      "ms_inverse_4x": parts["inverse"], "ms_obs_loop_7x": parts["obs_loop"], "tokens_per_hessian": tok,
+      "note": "value = fp32 weight bytes of the layer / (4 Hessians over 16384 tokens + 4 inverses + 7 OBS loops);"
+              " configs[4] uses 262144 tokens per Hessian: scale ms_hessian_4x by 16"}
   return out
 
 
