@@ -311,6 +311,167 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------ Cholesky, two-level variant
+// For large K the rank-32 trailing update is bound by the read-modify-write traffic of the
+// trailing matrix (K = 11008: 344 passes over up to 970 MB).  This variant updates the trailing
+// matrix once per outer block of CNB = 128 columns (a quarter of the passes) and factors the
+// 32-column panels of an outer block left-looking: a panel first applies the pending rank-(j - J)
+// update of the earlier panels of its outer block to its own 32 columns, then factors.  Its panel
+// step is slower than chol_panel (measured 65-92 us vs 43 us), so it only pays where the trailing
+// update dominates: the launcher takes it for K >= kCholTwoLevelMinK.
+constexpr int CNB = 128;   // outer block width
+constexpr int kCholTwoLevelMinK = 6144;
+
+// Panel at columns [j, j + CB), outer block starting at column J <= j (w = j - J pending columns).
+// Every CTA rebuilds the CB x CB diagonal block in shared memory (pending update included), warp 0
+// factors it in registers (lane r = row r; pivots and multipliers travel by shuffle), inverts the
+// factor, and each thread then forms its row of the panel as  (A[row, j:j+CB] - pending) * L_jj^-T
+// -- a dependency-free 32 x 32 product instead of a forward substitution.
+__global__ void __launch_bounds__(CR)
+    chol_panel2(double* __restrict__ A, int K, int j, int J, int* __restrict__ info) {
+  __shared__ double D[CB][CB + 1];          // diagonal block, then its Cholesky factor
+  __shared__ double Li[CB][CB + 1];         // inverse of the factor (lower triangular)
+  __shared__ double Pd[CB][CNB - CB + 1];   // pending columns of the diagonal block's rows
+  const int tid = threadIdx.x;
+  const int nb = min(CB, K - j);
+  const int w = j - J;
+  for (int e = tid; e < CB * CB; e += CR) {
+    const int r = e / CB, c = e % CB;
+    D[r][c] = (r < nb && c <= r) ? A[static_cast<long long>(j + r) * K + j + c] : (r == c ? 1.0 : 0.0);
+  }
+  for (int e = tid; e < CB * w; e += CR) {
+    const int r = e / w, k = e % w;
+    Pd[r][k] = r < nb ? A[static_cast<long long>(j + r) * K + J + k] : 0.0;
+  }
+  __syncthreads();
+  if (w > 0) {  // D -= Pd Pd^T on the lower triangle
+    for (int e = tid; e < CB * CB; e += CR) {
+      const int r = e / CB, c = e % CB;
+      if (c <= r && r < nb) {
+        double s = 0.0;
+        for (int k = 0; k < w; ++k) s = fma(Pd[r][k], Pd[c][k], s);
+        D[r][c] -= s;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {
+    const int lane = tid;
+    double a[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) a[c] = D[lane][c];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+      const double p = __shfl_sync(0xffffffffu, a[k], k);
+      if (lane == k && k < nb && !(p > 0.0)) atomicExch(info, j + k + 1);
+      const double sq = sqrt(p);
+      if (lane == k) a[k] = sq;
+      if (lane > k) a[k] = a[k] / sq;
+#pragma unroll
+      for (int c = k + 1; c < CB; ++c) {
+        const double lc = __shfl_sync(0xffffffffu, a[k], c);
+        if (lane >= c) a[c] = fma(-a[k], lc, a[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) D[lane][c] = (c <= lane) ? a[c] : 0.0;
+    __syncwarp();
+    // column `lane` of the inverse by forward substitution
+    double y[CB];
+#pragma unroll
+    for (int r = 0; r < CB; ++r) {
+      double sacc = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int m = 0; m < r; ++m) sacc = fma(-D[r][m], y[m], sacc);
+      y[r] = (r < lane) ? 0.0 : sacc / D[r][r];
+    }
+#pragma unroll
+    for (int r = 0; r < CB; ++r) Li[r][lane] = y[r];
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < CB * CB; e += CR) {
+      const int r = e / CB, c = e % CB;
+      if (r < nb && c < nb) A[static_cast<long long>(j + r) * K + j + c] = D[r][c];
+    }
+  }
+  const int row = j + nb + blockIdx.x * CR + tid;
+  if (row < K) {
+    double x[CB];
+    double* a = A + static_cast<long long>(row) * K + j;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) x[c] = c < nb ? a[c] : 0.0;
+    const double* pend = A + static_cast<long long>(row) * K + J;
+    for (int k = 0; k < w; ++k) {
+      const double v = pend[k];
+#pragma unroll
+      for (int c = 0; c < CB; ++c) x[c] = fma(-v, Pd[c][k], x[c]);
+    }
+    double o[CB];  // out[c] = sum_{m <= c} x[m] * Li[c][m]
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int m = 0; m <= c; ++m) sacc = fma(x[m], Li[c][m], sacc);
+      o[c] = sacc;
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < nb) a[c] = o[c];
+  }
+}
+
+// Trailing update A[r, c] -= sum_{k < depth} P[r, k] P[c, k] for the lower tiles of the trailing
+// matrix starting at row / column `base`, P = A[base:, J:J+depth]; 32-deep slabs.
+__global__ void __launch_bounds__(256)
+    chol_syrk2(double* __restrict__ A, int K, int J, int depth, int base) {
+  __shared__ double Pr[64][CB + 1];
+  __shared__ double Pc[64][CB + 1];
+  int tr = 0, left = blockIdx.x;
+  while (left > tr) {
+    left -= tr + 1;
+    ++tr;
+  }
+  const int tc = left;
+  const int r0 = base + tr * 64, c0 = base + tc * 64;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < depth; k0 += CB) {
+    if (k0 > 0) __syncthreads();
+    for (int e = tid; e < 64 * CB; e += 256) {
+      const int r = e / CB, k = e % CB;
+      const bool in = k0 + k < depth;
+      Pr[r][k] = (in && r0 + r < K) ? A[static_cast<long long>(r0 + r) * K + J + k0 + k] : 0.0;
+      Pc[r][k] = (in && c0 + r < K) ? A[static_cast<long long>(c0 + r) * K + J + k0 + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < CB; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = Pr[ty + 16 * u][k];
+        b[u] = Pc[tx + 16 * u][k];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + ty + 16 * u;
+    if (r >= K) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = c0 + tx + 16 * v;
+      if (c <= r) A[static_cast<long long>(r) * K + c] -= acc[u][v];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ triangular inverse (fp32, lower)
 constexpr int TB = 64;
 
@@ -596,13 +757,32 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   if (mutate_diagonal) {  // the reference leaves the damped diagonal in the caller's Hessian
     copy_diag_f64<<<(k + 255) / 256, 256, 0, st>>>(A, hessian, k); ++launches;
   }
-  for (int j = 0; j < k; j += CB) {
-    const int below = k - j - CB;
-    const unsigned pgrid = below > 0 ? static_cast<unsigned>((below + CR - 1) / CR) : 1u;
-    chol_panel<<<pgrid, CR, 0, st>>>(A, k, j, info); ++launches;
-    if (below > 0) {
-      const int nt = (below + 63) / 64;
-      chol_syrk<<<static_cast<unsigned>(nt * (nt + 1) / 2), 256, 0, st>>>(A, k, j); ++launches;
+  int two_level_min_k = kCholTwoLevelMinK;  // AEQB_CHOL_TWO_LEVEL_MIN_K: A/B runs and tests
+  if (const char* e2 = getenv("AEQB_CHOL_TWO_LEVEL_MIN_K")) two_level_min_k = atoi(e2);
+  if (k >= two_level_min_k) {
+    for (int J = 0; J < k; J += CNB) {
+      const int jend = J + CNB < k ? J + CNB : k;
+      for (int j = J; j < jend; j += CB) {
+        const int below = k - j - CB;
+        const unsigned pgrid = below > 0 ? static_cast<unsigned>((below + CR - 1) / CR) : 1u;
+        chol_panel2<<<pgrid, CR, 0, st>>>(A, k, j, J, info); ++launches;
+      }
+      const int below = k - jend;
+      if (below > 0) {
+        const int nt = (below + 63) / 64;
+        chol_syrk2<<<static_cast<unsigned>(nt * (nt + 1) / 2), 256, 0, st>>>(A, k, J, jend - J, jend);
+        ++launches;
+      }
+    }
+  } else {
+    for (int j = 0; j < k; j += CB) {
+      const int below = k - j - CB;
+      const unsigned pgrid = below > 0 ? static_cast<unsigned>((below + CR - 1) / CR) : 1u;
+      chol_panel<<<pgrid, CR, 0, st>>>(A, k, j, info); ++launches;
+      if (below > 0) {
+        const int nt = (below + 63) / 64;
+        chol_syrk<<<static_cast<unsigned>(nt * (nt + 1) / 2), 256, 0, st>>>(A, k, j); ++launches;
+      }
     }
   }
   lower_to_f32<<<cgrid, 256, 0, st>>>(A, L32, k); ++launches;

@@ -195,6 +195,30 @@ def test_hessian_inverse_property(cuda, k):
   np.testing.assert_allclose(damped @ got, np.eye(k), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("k", [31, 64, 200, 1024])
+def test_hessian_inverse_two_level_cholesky(cuda, monkeypatch, k):
+  """The large-K Cholesky variant (rank-128 trailing updates, left-looking panels; taken from
+  K = 6144 by default) forced onto oracle-sized orders: same bars as the default path."""
+  import torch
+  from aeq_b200 import device
+  monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", "1")
+  x = O.synthetic_activation((4, max(2 * k, 64), k), k + 1)
+  h = O.gptq_hessian(x)
+  if k == 31:
+    h[0, :] = 0.0
+    h[:, 0] = 0.0
+  got = device.hessian_inverse(torch.from_numpy(h.copy()).to(cuda), 0.01).cpu().numpy().astype(np.float64)
+  want = O.gptq_hessian_inverse(h.copy())
+  np.testing.assert_allclose(got, want, rtol=0, atol=1e-4 * np.abs(want).max())
+  hd = h.copy()
+  np.fill_diagonal(hd, O.gptq_damped_diagonal(h))
+  np.testing.assert_allclose(hd @ got, np.eye(k), rtol=0, atol=2e-3)
+  bad = np.eye(k)
+  bad[k // 2, k // 2] = -5.0
+  with pytest.raises(np.linalg.LinAlgError):
+    device.hessian_inverse(torch.from_numpy(bad).to(cuda), 0.0)
+
+
 def test_hessian_inverse_not_positive_definite(cuda):
   import torch
   from aeq_b200 import device
