@@ -316,22 +316,38 @@ __global__ void __launch_bounds__(256)
 // trailing matrix (K = 11008: 344 passes over up to 970 MB).  This variant updates the trailing
 // matrix once per outer block of CNB = 128 columns (a quarter of the passes) and factors the
 // 32-column panels of an outer block left-looking: a panel first applies the pending rank-(j - J)
-// update of the earlier panels of its outer block to its own 32 columns, then factors.  Its panel
-// step is slower than chol_panel (measured 65-92 us vs 43 us), so it only pays where the trailing
-// update dominates: the launcher takes it for K >= kCholTwoLevelMinK.
+// update of the earlier panels of its outer block to its own 32 columns, then factors.  Measured
+// (hessian_inverse, K = 4096 / 11008): single-level 10.4 / 91.4 ms, two-level 8.6 / 67.9 ms, so
+// it is the default (kCholTwoLevelMinK = 0; AEQB_CHOL_TWO_LEVEL_MIN_K selects the other one).
+// A 128 x 128 / 8 x 8-per-thread trailing update was measured slower than the 64 x 64 one
+// (10.3 / 84.9 ms): one CTA per SM with single-buffered slabs exposes the global-load latency.
 constexpr int CNB = 128;   // outer block width
-constexpr int kCholTwoLevelMinK = 6144;
+constexpr int kCholTwoLevelMinK = 0;
+constexpr int kCholPanel2Smem = CR * (CB + 1) * 8;  // dynamic: the row staging tile
 
 // Panel at columns [j, j + CB), outer block starting at column J <= j (w = j - J pending columns).
 // Every CTA rebuilds the CB x CB diagonal block in shared memory (pending update included), warp 0
 // factors it in registers (lane r = row r; pivots and multipliers travel by shuffle), inverts the
 // factor, and each thread then forms its row of the panel as  (A[row, j:j+CB] - pending) * L_jj^-T
 // -- a dependency-free 32 x 32 product instead of a forward substitution.
+// 1 / sqrt(p) in float64 from the fp32 estimate and two Newton steps (each step squares the
+// relative error: 2^-22 -> 2^-43 -> below 2^-53), a short dependent chain instead of the
+// software sqrt + divide (~600 cycles per pivot on the factorisation's critical path).
+__device__ __forceinline__ double rsqrt_f64(double p) {
+  double r = static_cast<double>(rsqrtf(static_cast<float>(p)));
+  r = r * fma(-0.5 * p, r * r, 1.5);
+  r = r * fma(-0.5 * p, r * r, 1.5);
+  return r;
+}
+
 __global__ void __launch_bounds__(CR)
     chol_panel2(double* __restrict__ A, int K, int j, int J, int* __restrict__ info) {
   __shared__ double D[CB][CB + 1];          // diagonal block, then its Cholesky factor
   __shared__ double Li[CB][CB + 1];         // inverse of the factor (lower triangular)
   __shared__ double Pd[CB][CNB - CB + 1];   // pending columns of the diagonal block's rows
+  extern __shared__ double chol_rt_raw[];   // staging tile: 32 columns of this CTA's 128 rows
+  double (*Rt)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chol_rt_raw);
+  __shared__ double rinv[CB];               // reciprocals of the factor's diagonal
   const int tid = threadIdx.x;
   const int nb = min(CB, K - j);
   const int w = j - J;
@@ -364,9 +380,14 @@ __global__ void __launch_bounds__(CR)
     for (int k = 0; k < CB; ++k) {
       const double p = __shfl_sync(0xffffffffu, a[k], k);
       if (lane == k && k < nb && !(p > 0.0)) atomicExch(info, j + k + 1);
-      const double sq = sqrt(p);
-      if (lane == k) a[k] = sq;
-      if (lane > k) a[k] = a[k] / sq;
+      const double rs = rsqrt_f64(p);
+      double sq = p * rs;
+      sq = fma(0.5 * rs, fma(-sq, sq, p), sq);  // one correction: sqrt(p) to the last bit or so
+      if (lane == k) {
+        a[k] = sq;
+        rinv[k] = rs;
+      }
+      if (lane > k) a[k] = a[k] * rs;
 #pragma unroll
       for (int c = k + 1; c < CB; ++c) {
         const double lc = __shfl_sync(0xffffffffu, a[k], c);
@@ -376,14 +397,18 @@ __global__ void __launch_bounds__(CR)
 #pragma unroll
     for (int c = 0; c < CB; ++c) D[lane][c] = (c <= lane) ? a[c] : 0.0;
     __syncwarp();
-    // column `lane` of the inverse by forward substitution
+    // column `lane` of the inverse by forward substitution, two partial sums per row
     double y[CB];
 #pragma unroll
     for (int r = 0; r < CB; ++r) {
-      double sacc = (r == lane) ? 1.0 : 0.0;
+      double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-      for (int m = 0; m < r; ++m) sacc = fma(-D[r][m], y[m], sacc);
-      y[r] = (r < lane) ? 0.0 : sacc / D[r][r];
+      for (int m = 0; m + 1 < r; m += 2) {
+        s0 = fma(-D[r][m], y[m], s0);
+        s1 = fma(-D[r][m + 1], y[m + 1], s1);
+      }
+      if (r & 1) s0 = fma(-D[r][r - 1], y[r - 1], s0);
+      y[r] = (r < lane) ? 0.0 : (s0 + s1) * rinv[r];
     }
 #pragma unroll
     for (int r = 0; r < CB; ++r) Li[r][lane] = y[r];
@@ -395,29 +420,44 @@ __global__ void __launch_bounds__(CR)
       if (r < nb && c < nb) A[static_cast<long long>(j + r) * K + j + c] = D[r][c];
     }
   }
-  const int row = j + nb + blockIdx.x * CR + tid;
-  if (row < K) {
-    double x[CB];
-    double* a = A + static_cast<long long>(row) * K + j;
-#pragma unroll
-    for (int c = 0; c < CB; ++c) x[c] = c < nb ? a[c] : 0.0;
-    const double* pend = A + static_cast<long long>(row) * K + J;
-    for (int k = 0; k < w; ++k) {
-      const double v = pend[k];
-#pragma unroll
-      for (int c = 0; c < CB; ++c) x[c] = fma(-v, Pd[c][k], x[c]);
+  // This CTA's CR rows below the diagonal block.  Global memory is only touched through the
+  // staging tile, 32 consecutive columns of a row per warp request (a thread per row reading its
+  // own row would scatter every request over 32 cache lines).
+  const long long row0 = static_cast<long long>(j) + nb + static_cast<long long>(blockIdx.x) * CR;
+  const int lane = tid & 31, wrp = tid >> 5;
+  auto stage_in = [&](int col0, int ncols) {  // Rt[r][c] = A[row0 + r][col0 + c]
+    __syncthreads();
+    for (int r = wrp; r < CR; r += CR / 32) {
+      const long long gr = row0 + r;
+      Rt[r][lane] = (gr < K && lane < ncols) ? A[gr * K + col0 + lane] : 0.0;
     }
-    double o[CB];  // out[c] = sum_{m <= c} x[m] * Li[c][m]
+    __syncthreads();
+  };
+  double x[CB];
+  stage_in(j, nb);
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      double sacc = 0.0;
+  for (int c = 0; c < CB; ++c) x[c] = Rt[tid][c];
+  for (int k0 = 0; k0 < w; k0 += CB) {
+    stage_in(J + k0, CB);
+#pragma unroll 4
+    for (int k = 0; k < CB; ++k) {
+      const double v = Rt[tid][k];
 #pragma unroll
-      for (int m = 0; m <= c; ++m) sacc = fma(x[m], Li[c][m], sacc);
-      o[c] = sacc;
+      for (int c = 0; c < CB; ++c) x[c] = fma(-v, Pd[c][k0 + k], x[c]);
     }
+  }
+  __syncthreads();
 #pragma unroll
-    for (int c = 0; c < CB; ++c)
-      if (c < nb) a[c] = o[c];
+  for (int c = 0; c < CB; ++c) {  // out[c] = sum_{m <= c} x[m] * Li[c][m]
+    double sacc = 0.0;
+#pragma unroll
+    for (int m = 0; m <= c; ++m) sacc = fma(x[m], Li[c][m], sacc);
+    Rt[tid][c] = sacc;
+  }
+  __syncthreads();
+  for (int r = wrp; r < CR; r += CR / 32) {
+    const long long gr = row0 + r;
+    if (gr < K && lane < nb) A[gr * K + j + lane] = Rt[r][lane];
   }
 }
 
@@ -760,12 +800,18 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   int two_level_min_k = kCholTwoLevelMinK;  // AEQB_CHOL_TWO_LEVEL_MIN_K: A/B runs and tests
   if (const char* e2 = getenv("AEQB_CHOL_TWO_LEVEL_MIN_K")) two_level_min_k = atoi(e2);
   if (k >= two_level_min_k) {
+    static bool panel2_configured = false;
+    if (!panel2_configured) {
+      e = cudaFuncSetAttribute(chol_panel2, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholPanel2Smem);
+      if (e != cudaSuccess) return e;
+      panel2_configured = true;
+    }
     for (int J = 0; J < k; J += CNB) {
       const int jend = J + CNB < k ? J + CNB : k;
       for (int j = J; j < jend; j += CB) {
         const int below = k - j - CB;
         const unsigned pgrid = below > 0 ? static_cast<unsigned>((below + CR - 1) / CR) : 1u;
-        chol_panel2<<<pgrid, CR, 0, st>>>(A, k, j, J, info); ++launches;
+        chol_panel2<<<pgrid, CR, kCholPanel2Smem, st>>>(A, k, j, J, info); ++launches;
       }
       const int below = k - jend;
       if (below > 0) {

@@ -196,12 +196,13 @@ def test_hessian_inverse_property(cuda, k):
 
 
 @pytest.mark.parametrize("k", [31, 64, 200, 1024])
-def test_hessian_inverse_two_level_cholesky(cuda, monkeypatch, k):
-  """The large-K Cholesky variant (rank-128 trailing updates, left-looking panels; taken from
-  K = 6144 by default) forced onto oracle-sized orders: same bars as the default path."""
+@pytest.mark.parametrize("min_k", ["0", "1000000"])
+def test_hessian_inverse_both_cholesky_variants(cuda, monkeypatch, k, min_k):
+  """The two-level Cholesky (rank-128 trailing updates, left-looking panels: the default) and the
+  single-level one (AEQB_CHOL_TWO_LEVEL_MIN_K above K) meet the same bars."""
   import torch
   from aeq_b200 import device
-  monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", "1")
+  monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", min_k)
   x = O.synthetic_activation((4, max(2 * k, 64), k), k + 1)
   h = O.gptq_hessian(x)
   if k == 31:
