@@ -107,6 +107,32 @@ def test_weight_only_inserts_dequantize_and_shares_buffers(cuda):
   assert _tensor(g, b"embedding/table").type == T.TensorType.FLOAT32               # FC-only recipe
 
 
+def test_dynamic_recipe_covers_embedding_and_regex_scopes(cuda):
+  """`*` expands to every op of the algorithm: the EMBEDDING_LOOKUP table is quantised per row
+  like an FC weight; a later scope entry overrides the blanket one for the layers it matches."""
+  from aeq_b200 import qtyping, quantizer, recipe
+  from aeq_b200.utils import tfl_flatbuffer_utils as fu
+  from aeq_b200.utils import tfl_model as T
+  table = O.synthetic_weight(100, 64, 5)
+  ws = [O.synthetic_weight(32, 64, 6), O.synthetic_weight(64, 32, 7)]
+  qz = quantizer.Quantizer(T.write_model_to_bytes(tfl_fixtures.fc_stack(ws, embedding=table)),
+                           recipe.dynamic_wi8_afp32())
+  qz.add_dynamic_config("layer1/", qtyping.TFLOperationName.FULLY_CONNECTED, 4)
+  m = T.read_model_from_bytes(qz.quantize().quantized_model)
+  g = m.subgraphs[0]
+  t = _tensor(g, b"embedding/table")
+  want = O.minmax_requant(table, 8, True)
+  assert t.type == T.TensorType.INT8 and t.quantization.quantizedDimension == 0
+  np.testing.assert_array_equal(fu.get_tensor_data(t, m.buffers), want["q"])
+  np.testing.assert_array_equal(t.quantization.scale, want["scale"].ravel())
+  assert _tensor(g, b"layer0/w").type == T.TensorType.INT8
+  w1 = _tensor(g, b"layer1/w")
+  assert w1.type == T.TensorType.INT4
+  np.testing.assert_array_equal(np.asarray(m.buffers[w1.buffer].data),
+                                O.pack_bits(4, O.minmax_requant(ws[1], 4, True)["q"]))
+  assert len(qz.get_quantization_recipe()) == 2
+
+
 def test_octav_int4_recipe_and_errors(cuda):
   from aeq_b200 import qtyping, quantizer
   from aeq_b200.utils import tfl_flatbuffer_utils as fu
