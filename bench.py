@@ -322,6 +322,45 @@ def extra_modes(dev, ws, peak, steps):
   return out
 
 
+def headline_8b(dev, peak):
+  """BASELINE.json's target set at full size on ONE GPU: 477 x [4096, 4096] fp32 = 8.00 B parameters =
+  32.0 GB resident in HBM, requantised per channel to INT8 and in blocks of 32 to
+  packed INT4; eight persistent launches of <= 64 tensors per pass."""
+  import torch
+  from aeq_b200 import device
+  n = 477
+  free, _ = torch.cuda.mem_get_info(dev)
+  if free < 60e9:
+    return {"headline_8b_params": {"skipped": f"only {free / 1e9:.0f} GB of HBM free"}}
+  g = torch.Generator(device=dev).manual_seed(8)
+  ws = []
+  for _ in range(n):
+    w = torch.randn(ROWS, COLS, device=dev, generator=g) * 0.02
+    w.view(-1)[::1024] *= 20.0
+    ws.append(w)
+  n_bytes = n * ROWS * COLS * 4
+  out = {}
+  for name, bpw, fn in (
+      ("int8_perchannel", 5.0, lambda st: device.requant_rows_batch(ws, 8, True, outs=st.get("o"))),
+      ("int4_block32_packed", 4.5625, lambda st: device.requant_blocks_batch(ws, 32, 4, outs=st.get("o")))):
+    st = {}
+    for _ in range(2):
+      st["o"] = fn(st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+      st["o"] = fn(st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out[name] = {"value": n_bytes / ms / 1e6, "ms_per_pass": ms,
+                 "roofline_frac": (n_bytes / 4) * bpw / ms / 1e6 / peak}
+    del st
+  return {"headline_8b_params": {"tensors": n, "fp32_bytes": n_bytes, "unit": "GB/s of fp32 weight bytes", **out}}
+
+
 def config_sets(dev, peak, reps):
   """BASELINE.json configs[2] and the weight side of configs[4] at their own tensor shapes
   (SURVEY.md §8d): the Gemma-2B FC set through INT4 block-32, the Llama-7B FC set through INT8 /
@@ -435,6 +474,8 @@ def config_sets(dev, peak, reps):
       parts["obs_loop"] += ms_q
     del hinv
   total = sum(parts.values())
+  del layer
+  out.update(headline_8b(dev, peak))
   out["cfg5_llama7b_layer_gptq_int4"] = {
       "value": lbytes / total / 1e6, "ms_per_layer": total, "ms_hessian_4x": parts["hessian"],
       "ms_inverse_4x": parts["inverse"], "ms_obs_loop_7x": parts["obs_loop"], "tokens_per_hessian": tok,
