@@ -632,6 +632,23 @@ def main():
   d2h = Te * (ROWS * COLS + ROWS * 8)
   # spot-check the e2e result against the device-resident path (same arithmetic)
   ok = bool((torch.from_numpy(e_outs[0][0]).to(dev) == state["r8"][0].q).all())
+  # what bounds the e2e arm: this box's host->device copy rate from pinned memory, measured with
+  # a device->host copy of a quarter of the bytes running beside it (the arm's own 4 : 1 mix)
+  pin_in = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+  pin_out = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+  d_in, d_out = torch.empty_like(pin_in, device=dev), torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+  s2 = torch.cuda.Stream()
+  best = 0.0
+  for _ in range(4):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d_in.copy_(pin_in, non_blocking=True)
+    with torch.cuda.stream(s2):
+      pin_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize()
+    best = max(best, pin_in.numel() / (time.perf_counter() - t0) / 1e9)
+  pcie_h2d = best
+  del pin_in, pin_out, d_in, d_out
 
   extra = {}
   if a.modes == "all" and rank == 0 and world == 1:
@@ -668,6 +685,8 @@ def main():
                      "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "tensors": Te, "ms_per_step": e2e_s * 1e3, "matches_device_path": ok,
+                "bound": "pcie", "h2d_gbs_measured": pcie_h2d,
+                "frac_of_h2d": (e2e_val / world) / pcie_h2d if pcie_h2d > 0 else None,
                 "api": "aeq_b200.host.requant_rows -> aeqb_host_requant_rows_batch_f32 (pinned host buffers)"},
         "cpu_baseline": cpu,
         "gpu_launches": int(launches8),
