@@ -127,17 +127,24 @@ __device__ __forceinline__ float div_row(float x, const RowQ& rq) {
 // Pass 2 of a tile whose rows are all symmetric / unclipped / inside the divide window.
 // Branch-free; partial tiles (row length not a multiple of NW chunks, tensor tails) compute their
 // unused chunk slots on zeros and predicate only the store.
-template <bool FULL, int NW, int SLOTS>
+template <bool FULL, bool CLAMP, int NW, int SLOTS>
 __device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const float2* by_slots,
-                                            int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks) {
+                                            int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks,
+                                            float lo, float hi) {
 #pragma unroll
   for (int j = 0; j < SLOTS; ++j) {
     const bool valid = FULL || warp + j * NW < nchunks;  // partial tiles: only the store is predicated
     const float2 by = by_slots[j];
     // The hoisted exact divide on the packed-fp32 pipe: two elements per FMUL2 / FFMA2
     // (same three roundings per element as the scalar sequence, so still bit-identical).
-    const float2 qa = div_fast2(make_float2(v[j].x, v[j].y), by.x, by.y);
-    const float2 qb = div_fast2(make_float2(v[j].z, v[j].w), by.x, by.y);
+    float2 qa = div_fast2(make_float2(v[j].x, v[j].y), by.x, by.y);
+    float2 qb = div_fast2(make_float2(v[j].z, v[j].w), by.x, by.y);
+    if (CLAMP) {
+      // Clipped rows (OCTAV, caller-supplied ranges): clamp(rint(t)) == rint(clamp(t)) for integer
+      // bounds, so the clip happens in the float domain and the magic-number rounding stays.
+      qa.x = fminf(fmaxf(qa.x, lo), hi); qa.y = fminf(fmaxf(qa.y, lo), hi);
+      qb.x = fminf(fmaxf(qb.x, lo), hi); qb.y = fminf(fmaxf(qb.y, lo), hi);
+    }
     if (ql) {
       const uint2 ra = rmagic2(qa, kMagic), rb = rmagic2(qb, kMagic);
       if (valid) *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) = bytes4(ra.x, ra.y, rb.x, rb.y);
@@ -347,15 +354,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
 
     // ---- pass 2: quantise from registers + store
     const bool all_fast = __all_sync(0xffffffffu, lane >= SLOTS || mine.mode == kFastSym);
-    if (all_fast && !(pp && bits != 4)) {
+    // symmetric rows with a live clamp (zero point 0, divisor inside the hoisted-divide window)
+    const bool all_clampable =
+        sym && __all_sync(0xffffffffu, lane >= SLOTS || (mine.mode != kSlow && mine.zp == 0.0f));
+    if ((all_fast || all_clampable) && !(pp && bits != 4)) {
       // Tight path: every row of the tile is symmetric / unclipped / in the divide
       // window.  (scale, reciprocal) per chunk slot via one broadcast LDS.64.
       if (lane < SLOTS) s_by[warp][lane] = make_float2(mine.b, mine.y);
       __syncwarp();
       int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
       uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
-      if (full_tile) tight_pass2<true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks);
-      else tight_pass2<false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks);
+      const float lo_f = static_cast<float>(qr.lo), hi_f = static_cast<float>(qr.hi);
+      if (all_fast) {
+        if (full_tile) tight_pass2<true, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else tight_pass2<false, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+      } else {
+        if (full_tile) tight_pass2<true, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else tight_pass2<false, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+      }
       __syncwarp();  // s_by[warp] is rewritten next tile
     } else {
 #pragma unroll
