@@ -62,6 +62,7 @@ SIGNATURES = {
     "aeqb_quantize_f32": (_I, [_P, _L, _L, _L, _P, _P, _I, _I, _I, _P, _P]),
     "aeqb_dequantize_f32": (_I, [_P, _I, _L, _L, _L, _P, _P, _I, _I, _P, _P]),
     "aeqb_pack_bits": (_I, [_P, _L, _I, _P, _P]),
+    "aeqb_requant_mse_rows_f32": (_I, [_P, _L, _L, _I, _F, _P, _P, _P, _P, _P]),
     "aeqb_dwr_workspace_bytes": (_c.c_size_t, [_L, _L]),
     "aeqb_dwr_scales_f32": (_I, [_P, _L, _L, _P, _P, _P]),
     "aeqb_max_abs_diff_f32": (_I, [_P, _P, _L, _P, _P, _P]),

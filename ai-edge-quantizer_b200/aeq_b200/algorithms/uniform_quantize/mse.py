@@ -2,8 +2,9 @@
 
 Mirror of ai_edge_quantizer/algorithms/uniform_quantize/mse.py
 (`_MSE_QUANT_MULS` :30-33, `get_tensor_quant_params` :36-128).  Device flow: one
-upload, `aeqb_mse_scale_rows_f32` (sum of squares per row / tensor), then
-`aeqb_quantize_f32` with that scale (zero point is int32 zeros, mse.py:109).
+upload, then per channel the fused `aeqb_requant_mse_rows_f32` (sum of squares, scale and
+integers in one pass); for a whole tensor `aeqb_mse_scale_rows_f32` followed by
+`aeqb_quantize_f32` (zero point is int32 zeros, mse.py:109).
 """
 from __future__ import annotations
 
@@ -56,8 +57,12 @@ def get_tensor_quant_params(
   else:
     raise NotImplementedError(
         f"MSE along quantised dimension {qdim} is not on the accelerated path yet")
-  scale = device.mse_scale_rows(x, multiplier)
-  q = device.quantize(x, scale.reshape(-1), None, cfg.num_bits, True, x.shape[0], x.shape[1])
+  if qdim == 0:  # per channel: scale and integers in one pass over the weight
+    out = device.requant_mse_rows(x, cfg.num_bits, multiplier)
+    scale, q = out.scale, out.q
+  else:          # whole tensor: grid-wide sum of squares first
+    scale = device.mse_scale_rows(x, multiplier)
+    q = device.quantize(x, scale.reshape(-1), None, cfg.num_bits, True, x.shape[0], x.shape[1])
   scale_np = hostio.to_host(scale).reshape(pshape)
   return qtyping.UniformQuantParams(
       scale=scale_np, zero_point=np.zeros_like(scale_np, dtype=np.int32), num_bits=cfg.num_bits,

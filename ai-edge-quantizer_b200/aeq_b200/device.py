@@ -350,6 +350,21 @@ def mse_scale_rows(x: torch.Tensor, multiplier: float) -> torch.Tensor:
   return scale
 
 
+def requant_mse_rows(x: torch.Tensor, bits: int, multiplier: float, want_q: bool = True,
+                     want_packed: bool = False) -> Requantized:
+  """MSE scale (k * RMS of the row) -> quantise, one HBM pass (aeqb_requant_mse_rows_f32)."""
+  _check_f32_2d(x)
+  rows, cols = x.shape
+  dev = x.device
+  q = torch.empty((rows, cols), dtype=torch.int8, device=dev) if want_q else None
+  packed = torch.empty(rows * cols * bits // 8, dtype=torch.uint8, device=dev) if want_packed else None
+  scale = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+  zp = torch.empty((rows, 1), dtype=torch.int32, device=dev)
+  _lib.call("aeqb_requant_mse_rows_f32", _ptr(x), rows, cols, bits, float(multiplier), _ptr(q),
+            _ptr(packed), _ptr(scale), _ptr(zp), _stream())
+  return Requantized(q, packed, scale, zp)
+
+
 def hadamard_rows(x: torch.Tensor, hadamard_size: int, out: Optional[torch.Tensor] = None):
   """x.reshape(-1, n) @ (H_n / sqrt(n)) along the last axis (aeqb_hadamard_rows_f32)."""
   _check_f32_2d(x)

@@ -558,4 +558,34 @@ int aeqb_oscar_quantize_f32(const float* w, int64_t n, int64_t d, int64_t group_
                "aeqb_oscar_quantize_f32");
 }
 
+int aeqb_requant_mse_rows_f32(const float* x, int64_t rows, int64_t cols, int bits, float multiplier,
+                              int8_t* q, uint8_t* packed, float* scale, int32_t* zp, void* stream) {
+  if (!bits_ok(bits)) return fail("num_bits must be 2, 4 or 8, got %d", bits);
+  if (rows < 0 || cols < 0 || cols > 0x7fffffff) return fail("bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+  if (rows == 0 || cols == 0) return 0;
+  if (!x || !scale) return fail("x / scale are NULL");
+  if (!(multiplier > 0.0f)) return fail("the MSE multiplier must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  aeqb::RowsJob j{};
+  j.x = x; j.q = q; j.packed = packed; j.scale = scale; j.zp = zp;
+  j.rows = rows; j.cols = static_cast<int>(cols);
+  j.mm_stride = j.clip_stride = j.out_stride = 1;
+  j.mse_k = multiplier;
+  if (aeqb::rows_job_class(j, bits) != 0)
+    return run_rows(&j, 1, {bits, 1}, st, "aeqb_requant_mse_rows_f32");
+  // unaligned / odd shapes: the two unfused kernels
+  if (packed) return fail("packed output needs 16-byte aligned rows of a multiple of 128 values");
+  if (int rc = check(aeqb::launch_mse_scale_rows(x, rows, cols, multiplier, scale, nullptr, sm_count(), st),
+                     "aeqb_requant_mse_rows_f32"))
+    return rc;
+  if (zp) {
+    if (int rc = check(cudaMemsetAsync(zp, 0, static_cast<size_t>(rows) * sizeof(int32_t), st),
+                       "aeqb_requant_mse_rows_f32"))
+      return rc;
+  }
+  if (!q) return 0;
+  return check(aeqb::launch_quantize(x, rows * cols, rows, cols, scale, nullptr, 1, bits, 1, q, sm_count(), st),
+               "aeqb_requant_mse_rows_f32");
+}
+
 }  // extern "C"

@@ -32,6 +32,7 @@ struct RowsJob {
   const float* given_max;
   const float* given_scale;  // optional final scale (uniform_quantize with caller parameters);
   const int32_t* given_zp;   //   its zero point, or null for zeros.  Index row * mm_stride.
+  float mse_k;               // != 0: scale = mse_k * sqrt(mean(row^2)) (mse.py:100-108), zero point 0
   long long rows;
   int cols;
   int rows_per_tile;            // launcher

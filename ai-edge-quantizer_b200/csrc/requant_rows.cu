@@ -174,6 +174,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
   __shared__ StageDesc desc[STAGES];
   __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
   __shared__ float2 s_by[NW][SLOTS];  // per-warp (scale, reciprocal) of each chunk slot
+  __shared__ double s_sq[3][NW * SLOTS];  // MSE mode: per-chunk sum of squares (fp64 sum of fp32 squares)
 
   const int tid = threadIdx.x;
   // Broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the per-chunk
@@ -243,13 +244,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     // at HBM speed) because it decides whether the hoisted divide may be used.
     const bool gscale = job.given_scale != nullptr;
     const bool given = job.given_min != nullptr && !gscale;
-    const bool abs_scan = gscale || sym;
+    const bool mse = job.mse_k != 0.0f;  // scale from the row's RMS; |x| max is still scanned (divide window)
+    const bool abs_scan = gscale || sym || mse;
 
     // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
     // atomic per chunk merges the row statistics (no row-change bookkeeping).
     const unsigned magic = job.cpr_magic;  // row of chunk c = (c * magic) >> 20
     const bool full_tile = nchunks == NW * SLOTS;
-    const bool plain = abs_scan && !given;
+    const bool plain = abs_scan && !given && !mse;
     float4 v[SLOTS];
     if (plain && full_tile) {  // branch-free common case
       // (Measured SLOWER on B200, 0.85-0.91 vs 0.92 of peak: folding the per-chunk atomics into
@@ -277,6 +279,43 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
         const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
         if (lane == 0 && valid) atomicMax(&s_acc[buf][r].amax_bits, m);
+      }
+    } else if (mse) {
+      // mse.get_tensor_quant_params (mse.py:100-108): fp32 squares summed in fp64.  A lane adds up
+      // the chunks of one row it sees in a run of consecutive slots and the warp reduces once per
+      // run (eight times fewer fp64 shuffles on 4096-wide rows); the run's total lands in the
+      // slot of its first chunk, zeros in the others, and the row is later summed in chunk
+      // order, so the result does not depend on timing.
+      double run = 0.0;
+      int run_c = warp, run_r = 0;
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) {
+        const int c = warp + j * NW;
+        const bool valid = c < nchunks;
+        v[j] = valid ? t4[c * 32 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
+        if (lane == 0 && valid) atomicMax(&s_acc[buf][r].amax_bits, m);
+        if (j > 0 && (r != run_r || !valid)) {  // warp-uniform: close the run
+          double t = run;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0 && run_c < nchunks) s_sq[buf][run_c] = t;
+          run = 0.0;
+          run_c = c;
+        } else if (j > 0 && lane == 0 && valid) {
+          s_sq[buf][c] = 0.0;
+        }
+        run_r = r;
+        double sq = static_cast<double>(__fmul_rn(v[j].x, v[j].x)) + static_cast<double>(__fmul_rn(v[j].y, v[j].y));
+        sq += static_cast<double>(__fmul_rn(v[j].z, v[j].z)) + static_cast<double>(__fmul_rn(v[j].w, v[j].w));
+        run += sq;
+      }
+      {
+        double t = run;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && run_c < nchunks) s_sq[buf][run_c] = t;
       }
     } else
 #pragma unroll
@@ -328,6 +367,21 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
       float mn, mx, xmax;
+      if (mse) {
+        double t = 0.0;
+        const int cfirst = r * cpr;
+        for (int k2 = 0; k2 < cpr; ++k2) t += s_sq[buf][cfirst + k2];
+        const float mean = __fdiv_rn(static_cast<float>(t), static_cast<float>(cols));
+        const float sc = __fmul_rn(jcopy.mse_k, __fsqrt_rn(mean));
+        xmax = __uint_as_float(s_acc[buf][r].amax_bits);
+        const DivBy dv = make_div(sc, xmax);
+        mine.b = sc; mine.y = dv.y; mine.zp = 0.0f;
+        mine.mode = dv.fast ? kFastClamp : kSlow;
+        if (my_c == r * cpr) {
+          if (jcopy.scale) jcopy.scale[grow * jcopy.out_stride] = sc;
+          if (jcopy.zp) jcopy.zp[grow * jcopy.out_stride] = 0;
+        }
+      } else {
       if (gscale) {
         mx = __uint_as_float(s_acc[buf][r].amax_bits);  // finalize_row only uses xmax here
         mn = -mx;
@@ -347,6 +401,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         xmax = max_nan(fabsf(mn), fabsf(mx));
       }
       mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c == r * cpr);
+      }
     }
     // Buffer (it+2)%3 was last read during the previous tile, which every warp has
     // left (they all passed the barrier above); it is next written two tiles from now.

@@ -274,6 +274,14 @@ AEQB_API int aeqb_dequantize_f32(const void* q, int q_bytes, int64_t n, int64_t 
  * lowest), odd tail zero padded.  out: ceil(n*bits/8) bytes.  bits 2 or 4. */
 AEQB_API int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* stream);
 
+/* mse.get_tensor_quant_params fused (algorithms/uniform_quantize/mse.py:36-128, per channel):
+ * scale[r] = multiplier * sqrt(mean(x[r]^2)) (fp32 squares, fp64 sum, fp32 mean / sqrt /
+ * multiply), zero point 0, q = clip(rint(x / scale)) with the symmetric range, in ONE pass
+ * over x (4 B read + 1 B written per weight).  q / packed / zp may be NULL. */
+AEQB_API int aeqb_requant_mse_rows_f32(const float* x, int64_t rows, int64_t cols, int bits,
+                                       float multiplier, int8_t* q, uint8_t* packed, float* scale,
+                                       int32_t* zp, void* stream);
+
 /* ---------------------------------------------------------------- recovery / casting
  * dequantized_weight_recovery.get_zp_scale_from_dequantized_symmetric_weights
  * (algorithms/uniform_quantize/dequantized_weight_recovery.py:132-217): for each of n_groups

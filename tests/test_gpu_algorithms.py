@@ -173,6 +173,35 @@ def test_mse_vs_oracle_and_errors(cuda):
     _run(mse, O.synthetic_weight(4, 64, 1), _cfg(2, 0))
 
 
+@pytest.mark.parametrize("shape", [(96, 4096), (9, 11008), (40, 1536), (3, 16384), (130, 256)])
+def test_mse_fused_equals_unfused(cuda, shape):
+  """aeqb_requant_mse_rows_f32 (one pass) against aeqb_mse_scale_rows_f32 + aeqb_quantize_f32 and the
+  oracle: same fp64 sum of fp32 squares up to association, so scales are equal to 1 ulp at worst
+  and bit-equal here; degenerate rows (all zero -> scale 0 -> q 0, NaN -> q 0) follow the reference."""
+  import torch
+  from aeq_b200 import device
+  w = O.synthetic_weight(*shape, index=shape[1] % 23)
+  w[1, :] = 0.0
+  if shape[0] > 4:
+    w[3, 5] = np.nan
+  x = torch.from_numpy(w).to(cuda)
+  for bits, k in ((8, 0.05408), (4, 0.37755)):
+    fused = device.requant_mse_rows(x, bits, k, want_packed=(bits == 4))
+    scale = device.mse_scale_rows(x, k)
+    q = device.quantize(x, scale.reshape(-1), None, bits, True, shape[0], shape[1])
+    np.testing.assert_array_equal(fused.scale.cpu().numpy().ravel(), scale.cpu().numpy().ravel())
+    np.testing.assert_array_equal(fused.q.cpu().numpy(), q.cpu().numpy())
+    assert not fused.zero_point.any()
+    if bits == 4:
+      np.testing.assert_array_equal(fused.packed.cpu().numpy(), O.pack_bits(4, fused.q.cpu().numpy()))
+    with np.errstate(all="ignore"):
+      ref = O.mse_requant(w, bits)
+    ok = np.isfinite(ref["scale"]).ravel()
+    np.testing.assert_allclose(fused.scale.cpu().numpy().ravel()[ok], ref["scale"].ravel()[ok], rtol=1e-6)
+    _assert_ints(fused.q.cpu().numpy(), ref["q"])
+    assert not fused.q.cpu().numpy()[1].any()
+
+
 def test_hadamard_golden(cuda):
   from aeq_b200.algorithms.uniform_quantize import hadamard_rotation as had
   z, cases = _cases("hadamard")
