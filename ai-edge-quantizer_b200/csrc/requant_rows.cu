@@ -163,7 +163,11 @@ __device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const floa
 // SLOTS = chunk slots (128 floats each) per consumer warp and tile, STAGES = depth of the ring.
 // Classes 1-3 use 8 slots and 3 stages; the wide class (4) uses 12 slots and 2 stages of 96 KiB so
 // that one round trip of a CTA moves up to 96 KiB (two 44 KiB rows, four 24 KiB rows).
-template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
+// RICH = false is the min/max hot path exactly; RICH = true adds the modes whose extra code and
+// shared memory measurably slow that path down when compiled into it (0.96 -> 0.92 of peak):
+// the RMS row statistic of MSE and the clamped tight pass 2 of clipped / given-scale rows.  The
+// launcher picks the instantiation per batch.
+template <int STAGE_BYTES, int NW, int SLOTS, int STAGES, bool RICH>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1)))
     requant_rows_stream(const __grid_constant__ RowsBatch b) {
   static_assert(STAGE_BYTES / (kChunk * 4) == NW * SLOTS, "chunks per warp");
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
   __shared__ StageDesc desc[STAGES];
   __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
   __shared__ float2 s_by[NW][SLOTS];  // per-warp (scale, reciprocal) of each chunk slot
-  __shared__ double s_sq[3][NW * SLOTS];  // MSE mode: per-chunk sum of squares (fp64 sum of fp32 squares)
+  __shared__ double s_sq[RICH ? 3 : 1][RICH ? NW * SLOTS : 1];  // MSE: per-chunk fp64 sums of fp32 squares
 
   const int tid = threadIdx.x;
   // Broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the per-chunk
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     // at HBM speed) because it decides whether the hoisted divide may be used.
     const bool gscale = job.given_scale != nullptr;
     const bool given = job.given_min != nullptr && !gscale;
-    const bool mse = job.mse_k != 0.0f;  // scale from the row's RMS; |x| max is still scanned (divide window)
+    const bool mse = RICH && job.mse_k != 0.0f;  // scale from the row's RMS; |x| max still scanned (divide window)
     const bool abs_scan = gscale || sym || mse;
 
     // ---- pass 1: pull this warp's chunks into registers; one REDUX + one shared
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
         if (lane == 0 && valid) atomicMax(&s_acc[buf][r].amax_bits, m);
       }
-    } else if (mse) {
+    } else if (RICH && mse) {
       // mse.get_tensor_quant_params (mse.py:100-108): fp32 squares summed in fp64.  A lane adds up
       // the chunks of one row it sees in a run of consecutive slots and the warp reduces once per
       // run (eight times fewer fp64 shuffles on 4096-wide rows); the run's total lands in the
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
       float mn, mx, xmax;
-      if (mse) {
+      if (RICH && mse) {
         double t = 0.0;
         const int cfirst = r * cpr;
         for (int k2 = 0; k2 < cpr; ++k2) t += s_sq[buf][cfirst + k2];
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     const bool all_fast = __all_sync(0xffffffffu, lane >= SLOTS || mine.mode == kFastSym);
     // symmetric rows with a live clamp (zero point 0, divisor inside the hoisted-divide window)
     const bool all_clampable =
-        sym && __all_sync(0xffffffffu, lane >= SLOTS || (mine.mode != kSlow && mine.zp == 0.0f));
+        RICH && sym && __all_sync(0xffffffffu, lane >= SLOTS || (mine.mode != kSlow && mine.zp == 0.0f));
     if ((all_fast || all_clampable) && !(pp && bits != 4)) {
       // Tight path: every row of the tile is symmetric / unclipped / in the divide
       // window.  (scale, reciprocal) per chunk slot via one broadcast LDS.64.
@@ -420,10 +424,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
       int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
       uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
       const float lo_f = static_cast<float>(qr.lo), hi_f = static_cast<float>(qr.hi);
-      if (all_fast) {
+      if (!RICH || all_fast) {
         if (full_tile) tight_pass2<true, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
         else tight_pass2<false, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
-      } else {
+      } else if constexpr (RICH) {
         if (full_tile) tight_pass2<true, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
         else tight_pass2<false, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
       }
@@ -534,9 +538,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
-cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
-  auto kern = requant_rows_stream<STAGE_BYTES, NW, SLOTS, STAGES>;
+template <int STAGE_BYTES, int NW, int SLOTS, int STAGES, bool RICH>
+cudaError_t launch_stream_as(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
+  auto kern = requant_rows_stream<STAGE_BYTES, NW, SLOTS, STAGES, RICH>;
   const int smem = STAGES * STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -548,6 +552,17 @@ cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cud
   if (grid > b.n_tiles) grid = b.n_tiles;
   kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
   return count_launch();
+}
+
+// Plain min/max batches take the lean instantiation; anything with an RMS statistic, clipping
+// constants or caller-supplied scales takes the rich one.
+template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
+cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
+  bool rich = false;
+  for (int i = 0; i < b.n_jobs; ++i)
+    rich |= b.jobs[i].mse_k != 0.0f || b.jobs[i].clip != nullptr || b.jobs[i].given_scale != nullptr;
+  return rich ? launch_stream_as<STAGE_BYTES, NW, SLOTS, STAGES, true>(b, sm_count, ctas_per_sm, st)
+              : launch_stream_as<STAGE_BYTES, NW, SLOTS, STAGES, false>(b, sm_count, ctas_per_sm, st);
 }
 
 }  // namespace
