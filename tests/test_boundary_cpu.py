@@ -209,6 +209,33 @@ def test_product_path_fails_loudly_without_gpu():
     nmm.get_tensor_quant_params(sg.op_info(op, cfg), cfg, w, None)
 
 
+def test_every_algorithm_and_the_quantizer_fail_loudly_without_gpu():
+  """No algorithm has a host fallback: every weight path and the Quantizer front end raise on a
+  box without a CUDA device instead of computing on the CPU."""
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  from aeq_b200 import quantizer, recipe
+  from aeq_b200.algorithms.nonlinear_quantize import float_casting
+  from aeq_b200.algorithms.uniform_quantize import (dequantized_weight_recovery, gptq, hadamard_rotation,
+                                                    mse, octav, oscar)
+  from aeq_b200.utils import tfl_model as T
+  from tests import tfl_fixtures
+  w = np.ones((8, 64), np.float32)
+  op, _ = sg.fc_graph(w)
+  cfg = qtyping.TensorQuantizationConfig(8, True, G.CHANNELWISE)
+  qsv = {"activation_tensor_qsv": {"hessian": np.eye(64), "num_samples": 1}}
+  for mod, q in ((octav, None), (mse, None), (hadamard_rotation, None), (oscar, None),
+                 (dequantized_weight_recovery, None), (gptq, qsv)):
+    with pytest.raises((RuntimeError, ImportError), match="no CPU fallback|CUDA"):
+      mod.get_tensor_quant_params(sg.op_info(op, cfg), cfg, w, q)
+  with pytest.raises((RuntimeError, ImportError), match="no CPU fallback|CUDA"):
+    float_casting.cast_weight(w)
+  model = T.write_model_to_bytes(tfl_fixtures.fc_stack([w]))
+  with pytest.raises(ValueError, match="no CPU fallback|CUDA"):  # wrapped with the tensor's name
+    quantizer.Quantizer(model, recipe.dynamic_wi8_afp32()).quantize()
+
+
 def test_product_never_imports_oracle():
   import os
   import re
