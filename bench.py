@@ -680,7 +680,7 @@ def main():
                                     "bytes_per_weight": 4.5625}, **extra},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "requant_rows_stream<16384,4,8,3>", "bytes_per_weight": 5.0,
+                     "kernel": "requant_rows_stream<16384,4,8,3,false>", "bytes_per_weight": 5.0,
                      "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": k_ms,
                      "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
