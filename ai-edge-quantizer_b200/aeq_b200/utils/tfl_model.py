@@ -10,8 +10,8 @@ public TFLite schema (schema.fbs, file identifier TFL3).
 Scope: everything the quantizer reads or rewrites is parsed into attributes.  Operator option
 tables (`builtin_options`) are carried through as opaque scalar-only tables, which is what all
 but a handful of them are; the ones holding vectors are handled explicitly (Reshape, Squeeze,
-ConcatEmbeddings) or rejected at write time (VarHandle, Bucketize, and the StableHLO
-`builtin_options_2` family), as are sparsity and variant tensors.  Constant data is exposed as
+ConcatEmbeddings, and StableHLOCompositeOptions of `builtin_options_2`) or rejected at write time
+(VarHandle, Bucketize, the other StableHLO options), as are sparsity and variant tensors.  Constant data is exposed as
 zero-copy views of the input bytes (mmap-friendly: nothing is copied at read time).
 """
 from __future__ import annotations
@@ -83,6 +83,19 @@ class ConcatEmbeddingsOptions:
   numChannels: int = 0
   numColumnsPerChannel: Optional[np.ndarray] = None
   embeddingDimPerChannel: Optional[np.ndarray] = None
+
+
+@dataclasses.dataclass(eq=False)
+class StableHLOCompositeOptionsT:
+  """builtin_options_2 member 21 (STABLEHLO_COMPOSITE ops: `odml.*` fused subgraphs)."""
+  name: Optional[bytes] = None
+  decompositionSubgraphIndex: int = 0
+  compositeAttributes: Optional[np.ndarray] = None
+  compositeAttributesFormat: int = 0
+  version: int = 0
+
+
+_OPT2_STABLEHLO_COMPOSITE = 21
 
 
 @dataclasses.dataclass(eq=False)
@@ -242,7 +255,12 @@ def _read_operator(t: fb.Table) -> OperatorT:
       largeCustomOptionsOffset=t.scalar(9, "ulong"), largeCustomOptionsSize=t.scalar(10, "ulong"),
       builtinOptions2Type=t.scalar(11, "ubyte"), debugMetadataIndex=t.scalar(13, "int", -1))
   if t.has(12):
-    op.builtinOptions2 = True  # StableHLO options: present, not modelled (rejected at write time)
+    if op.builtinOptions2Type == _OPT2_STABLEHLO_COMPOSITE:
+      o = t.table(12)
+      op.builtinOptions2 = StableHLOCompositeOptionsT(
+          o.string(0), o.scalar(1, "int"), o.scalar_vector(2, "ubyte"), o.scalar(3, "byte"), o.scalar(4, "int"))
+    else:
+      op.builtinOptions2 = True  # other StableHLO options: present, not modelled (rejected at write time)
   return op
 
 
@@ -371,8 +389,20 @@ def _write_options(b: fb.Builder, kind: int, opt) -> int:
 
 
 def _write_operator(b: fb.Builder, op: OperatorT) -> int:
-  if op.builtinOptions2 is not None:
-    raise NotImplementedError("builtin_options_2 (StableHLO) operators are not serialised by aeq_b200")
+  opts2 = 0
+  if isinstance(op.builtinOptions2, StableHLOCompositeOptionsT):
+    o = op.builtinOptions2
+    name, attrs = _str(b, o.name), _vec(b, o.compositeAttributes, np.uint8)
+    b.start_table()
+    b.add_offset(0, name)
+    b.add_scalar(1, "int", int(o.decompositionSubgraphIndex))
+    b.add_offset(2, attrs)
+    b.add_scalar(3, "byte", int(o.compositeAttributesFormat))
+    b.add_scalar(4, "int", int(o.version))
+    opts2 = b.end_table()
+  elif op.builtinOptions2 is not None:
+    raise NotImplementedError(
+        f"builtin_options_2 type {op.builtinOptions2Type} (StableHLO) is not serialised by aeq_b200")
   ins, outs = _vec(b, op.inputs, np.int32), _vec(b, op.outputs, np.int32)
   opts = _write_options(b, op.builtinOptionsType, op.builtinOptions)
   custom = _vec(b, op.customOptions, np.uint8)
@@ -391,6 +421,9 @@ def _write_operator(b: fb.Builder, op: OperatorT) -> int:
   b.add_offset(8, inter)
   b.add_scalar(9, "ulong", int(op.largeCustomOptionsOffset))
   b.add_scalar(10, "ulong", int(op.largeCustomOptionsSize))
+  if opts2:
+    b.add_scalar(11, "ubyte", int(op.builtinOptions2Type))
+    b.add_offset(12, opts2)
   b.add_scalar(13, "int", int(op.debugMetadataIndex), -1)
   return b.end_table()
 

@@ -114,8 +114,8 @@ def test_synthetic_model_roundtrip():
 
 @pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="reference tree not mounted")
 def test_reference_fixtures_roundtrip():
-  """Every .tflite the reference ships parses, and re-serialises to an identical object tree
-  (two StableHLO-composite models are rejected at write time by design)."""
+  """Every .tflite the reference ships parses and re-serialises to an identical object tree,
+  the two StableHLO-composite models included."""
   files = sorted(glob.glob(os.path.join(REF_MODELS, "**", "*.tflite"), recursive=True))
   assert len(files) >= 70
   ok, rejected = 0, []
@@ -128,7 +128,10 @@ def test_reference_fixtures_roundtrip():
       continue
     _same(m, T.read_model_from_bytes(out), os.path.basename(f))
     ok += 1
-  assert sorted(rejected) == ["sdpa_composite.tflite", "simple_composite.tflite"] and ok >= 68
+  assert rejected == [] and ok == len(files)
+  comp = T.read_model(os.path.join(REF_MODELS, "sdpa_composite.tflite")).subgraphs[0].operators[5]
+  assert comp.builtinOptions2Type == 21 and comp.builtinOptions2.name == b"odml.scaled_dot_product_attention"
+  assert comp.builtinOptions2.decompositionSubgraphIndex == 1 and comp.builtinOptions2.compositeAttributes.size == 28
   m = T.read_model(os.path.join(REF_MODELS, "single_fc.tflite"))
   g = m.subgraphs[0]
   op = g.operators[0]
