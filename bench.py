@@ -151,7 +151,7 @@ def run_reference(a):
   v1 = 2 * ROWS * COLS * 4 / (time.perf_counter() - t1) / 1e9
   sample = (f"{n} of the workload's [{ROWS},{COLS}] tensors per step, {steps} steps,"
             f" {threads} threads over independent tensors")
-  print(json.dumps({
+  emit(({
       "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
       "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -166,7 +166,7 @@ def run_reference(a):
               " bit-exact to the reference; the Python reference cannot travel to the GPU box)."
               " The reference is single-threaded NumPy on this path; this arm additionally runs"
               " independent tensors on every host core",
-  }), flush=True)
+  }))
 
 
 # ------------------------------------------------------------------ clocks
@@ -485,8 +485,31 @@ def config_sets(dev, peak, reps):
 
 
 # ------------------------------------------------------------------ GPU arm
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+  """stdout must carry exactly ONE JSON line.  Libraries print there too (NCCL writes
+  "NCCL version ..." with a bare printf when NCCL_DEBUG=VERSION), so file descriptor 1 is pointed
+  at stderr for the whole run and the result is written to a duplicate of the original stdout."""
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+  line = (json.dumps(obj) + "\n").encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(line.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_REAL_STDOUT, line)
+
+
 def main():
   a = parse()
+  quiet_stdout()
   if a.impl == "reference":
     run_reference(a)
     return
@@ -503,6 +526,9 @@ def main():
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
+    # stdout carries exactly one JSON line: NCCL's own log lines ("NCCL version ...", INFO output
+    # when the caller asks for it) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
   lib = _lib.load()
 
@@ -665,7 +691,7 @@ def main():
            "host_cores": os.cpu_count()}
 
   if rank == 0:
-    print(json.dumps({
+    emit(({
         "metric": METRIC, "value": value8, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms8, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -691,7 +717,7 @@ def main():
         "cpu_baseline": cpu,
         "gpu_launches": int(launches8),
         "clocks": clocks,
-    }), flush=True)
+    }))
   if world > 1:
     dist.destroy_process_group()
 
