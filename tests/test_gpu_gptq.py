@@ -261,6 +261,29 @@ def test_column_loop_same_hinv_vs_oracle(cuda):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
 
 
+def test_column_loop_divide_window_fallback(cuda):
+  """The column kernel divides through hoisted reciprocals only inside the window where that is
+  provably the IEEE quotient; rows outside it (an all-zero row: scale 1e-9 / 7 is below 2^-30, a
+  row of 1e30s: errors above 2^90) are redone with IEEE divides.  Single block: bit-exact."""
+  import torch
+  from aeq_b200 import device
+  w = O.synthetic_weight(24, 64, 11)
+  w[1, :] = 0.0
+  w[2, :] = 1e30
+  w[3, :8] = 1e-38
+  x = O.synthetic_activation((2, 200, 64), 11)
+  hinv = O.gptq_hessian_inverse(O.gptq_hessian(x))
+  for sym in (True, False):
+    mn, mx = O.weight_minmax(w, 0, True)
+    zp, scale = O.scale_zp(mn, mx, 4, sym, False)
+    with np.errstate(all="ignore"):
+      want = O.gptq_quantize(w, scale, zp, hinv, 4, sym)
+    got = device.gptq_quantize(torch.from_numpy(w).to(cuda), torch.from_numpy(hinv).to(cuda),
+                               torch.from_numpy(scale.reshape(-1)).to(cuda),
+                               torch.from_numpy(zp.astype(np.int32).reshape(-1)).to(cuda), 0, 4, sym)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
 def test_gptq_golden_end_to_end(cuda):
   from aeq_b200.algorithms.uniform_quantize import gptq
   z = np.load(GOLD)
