@@ -18,6 +18,8 @@
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
+#include <cstdlib>
+
 namespace aeqb {
 
 namespace {
@@ -192,6 +194,162 @@ cudaError_t launch_reg(const float* x, long long rows, int cols, int n, float no
   return count_launch();
 }
 
+// ------------------------------------------------------------------ 4096-float tiles, one warp each
+// n = 128..4096 with the tensor a whole number of 16 KiB tiles: a warp owns a tile (1..32 whole
+// segments) and keeps it in 128 registers per lane.  The tile arrives by ONE 16 KiB bulk copy
+// (cp.async.bulk + mbarrier; the next tile is queued as soon as this one sits in registers) and
+// leaves by 32 bulk stores of 512 B, so the warp issues no global loads or stores itself and HBM
+// latency never reaches the scoreboard.  Element index e = 12 bits:
+//   map 1 (after the load):   float4 slot j*32 + lane  -> registers hold e[1:0] and e[11:7]
+//   map 2 (after the exchange): float4 slot lane*32 + k -> registers hold e[6:0]
+// so stages 1, 2 and 128..n/2 run in map 1, stages 4..64 in map 2, every butterfly on packed
+// fp32 pairs (FADD2 / FFMA2, half an issue slot per add) except stage 1.  The one exchange goes
+// through a shared-memory tile whose 512-byte rows are padded to 528 bytes: both access patterns
+// are conflict-free 128-bit accesses, and a row is exactly one lane's output run, which that
+// lane hands to the bulk-store engine.  8.3 issue slots per element instead of 33.
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {  // a - b: b * -1 is exact, one rounding
+  return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+}
+
+constexpr int kTileFloats = 4096;
+constexpr int kTileWarps = 2;                       // warps per CTA, each with its own buffers
+constexpr int kTileLandBytes = kTileFloats * 4;     // bulk-copy landing buffer
+constexpr int kTileRowF4 = 33;                      // 32 float4 + 1 pad per exchange row
+constexpr int kTileXchgBytes = 32 * kTileRowF4 * 16;
+constexpr int kTileSmemPerWarp = kTileLandBytes + kTileXchgBytes;
+
+template <int LOG2N>
+__global__ void __launch_bounds__(kTileWarps * 32, 3)
+    hadamard_tiles(const float* __restrict__ x, long long ntiles, float norm, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) uint64_t s_bar[kTileWarps];
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  unsigned char* base = s_raw + static_cast<size_t>(warp) * kTileSmemPerWarp;
+  const float4* land = reinterpret_cast<const float4*>(base);
+  float4* xchg = reinterpret_cast<float4*>(base + kTileLandBytes);
+  uint64_t* bar = &s_bar[warp];
+  const long long stride = static_cast<long long>(gridDim.x) * kTileWarps;
+  long long tile = static_cast<long long>(blockIdx.x) * kTileWarps + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (tile < ntiles) {
+      mbar_arrive_expect_tx(bar, kTileLandBytes);
+      bulk_g2s(base, x + tile * kTileFloats, kTileLandBytes, bar);
+    }
+  }
+  __syncwarp();
+  unsigned parity = 0;
+  for (; tile < ntiles; tile += stride) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    float2 lo[32], hi[32];  // float4 slot = (lo, hi)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 v = land[j * 32 + lane];
+      lo[j] = make_float2(v.x, v.y);
+      hi[j] = make_float2(v.z, v.w);
+    }
+    __syncwarp();  // the landing buffer is drained: queue the next tile into it
+    if (lane == 0 && tile + stride < ntiles) {
+      mbar_arrive_expect_tx(bar, kTileLandBytes);
+      bulk_g2s(base, x + (tile + stride) * kTileFloats, kTileLandBytes, bar);
+    }
+    // ---- map 1: stages 1 and 2 inside a float4, stages 128..n/2 across slots
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float2 a = make_float2(lo[j].x + lo[j].y, lo[j].x - lo[j].y);
+      const float2 b = make_float2(hi[j].x + hi[j].y, hi[j].x - hi[j].y);
+      lo[j] = add2(a, b);
+      hi[j] = sub2(a, b);
+    }
+#pragma unroll
+    for (int hb = 1; hb < (1 << (LOG2N - 7)); hb <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if ((j & hb) == 0) {
+          const float2 a0 = lo[j], a1 = hi[j], b0 = lo[j | hb], b1 = hi[j | hb];
+          lo[j] = add2(a0, b0); hi[j] = add2(a1, b1);
+          lo[j | hb] = sub2(a0, b0); hi[j | hb] = sub2(a1, b1);
+        }
+      }
+    }
+    // the previous tile's bulk stores must have read the exchange rows before they are rewritten
+    bulk_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      xchg[j * kTileRowF4 + lane] = make_float4(lo[j].x, lo[j].y, hi[j].x, hi[j].y);
+    __syncwarp();
+    // ---- map 2: lane owns 128 consecutive floats; stages 4..64 across its 32 slots
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float4 v = xchg[lane * kTileRowF4 + k];
+      lo[k] = make_float2(v.x, v.y);
+      hi[k] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int hb = 1; hb < 32; hb <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if ((k & hb) == 0) {
+          const float2 a0 = lo[k], a1 = hi[k], b0 = lo[k | hb], b1 = hi[k | hb];
+          lo[k] = add2(a0, b0); hi[k] = add2(a1, b1);
+          lo[k | hb] = sub2(a0, b0); hi[k | hb] = sub2(a1, b1);
+        }
+      }
+    }
+    const float2 nn = make_float2(norm, norm);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float2 p = __fmul2_rn(lo[k], nn), q = __fmul2_rn(hi[k], nn);
+      xchg[lane * kTileRowF4 + k] = make_float4(p.x, p.y, q.x, q.y);  // the lane's own row
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+    bulk_s2g(out + tile * kTileFloats + lane * 128, xchg + lane * kTileRowF4, 512);
+    bulk_commit();
+  }
+  bulk_wait_read0();  // shared memory must outlive the last stores' reads
+}
+
+template <int LOG2N>
+cudaError_t launch_tiles_k(const float* x, long long ntiles, float norm, float* out, int sm_count,
+                           cudaStream_t st) {
+  constexpr int smem = kTileWarps * kTileSmemPerWarp;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hadamard_tiles<LOG2N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hadamard_tiles<LOG2N>,
+                                                                kTileWarps * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sm_count) * per_sm;
+  const long long need = (ntiles + kTileWarps - 1) / kTileWarps;
+  if (grid > need) grid = need;
+  hadamard_tiles<LOG2N><<<static_cast<unsigned>(grid), kTileWarps * 32, smem, st>>>(x, ntiles, norm,
+                                                                                    out);
+  return count_launch();
+}
+
 // Fallback for rows longer than 64 KiB or unaligned / odd shapes: one butterfly
 // stage per launch, in place in global memory (`buf` already holds a copy of x).
 __global__ void __launch_bounds__(256)
@@ -222,6 +380,19 @@ cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols,
   const float norm = 1.0f / sqrtf(static_cast<float>(n));
   const bool smem_ok = cols <= 16384 && cols % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
                        reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  static const bool no_tiles = getenv("AEQB_HADAMARD_NO_TILES") != nullptr;  // A/B runs
+  if (!no_tiles && n >= 256 && n <= kTileFloats && (rows * cols) % kTileFloats == 0 &&
+      reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    // segments are consecutive n-float runs of the flattened tensor: 16 KiB tiles hold whole ones
+    const long long ntiles = rows * cols / kTileFloats;
+    switch (n) {
+      case 256: return launch_tiles_k<8>(x, ntiles, norm, out, sm_count, st);
+      case 512: return launch_tiles_k<9>(x, ntiles, norm, out, sm_count, st);
+      case 1024: return launch_tiles_k<10>(x, ntiles, norm, out, sm_count, st);
+      case 2048: return launch_tiles_k<11>(x, ntiles, norm, out, sm_count, st);
+      default: return launch_tiles_k<12>(x, ntiles, norm, out, sm_count, st);
+    }
+  }
   if (smem_ok && cols % 256 == 0 && n <= 8192) {  // n = 16384 would need 256 data registers
     const int c = static_cast<int>(cols), nn = static_cast<int>(n);
     switch (n > 256 ? nn / 256 : 1) {

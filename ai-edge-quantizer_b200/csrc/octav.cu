@@ -25,6 +25,8 @@
 #include "aeqb_common.cuh"
 #include "aeqb_kernels.h"
 
+#include <cstdlib>
+
 namespace aeqb {
 
 namespace {
@@ -72,7 +74,7 @@ __device__ __forceinline__ float mask_ge(float a, float g) {
 
 __device__ __forceinline__ float condition(float x, int& zeros) {
   zeros += (x == 0.0f);
-  return (x == x) ? fabsf(x) : -1.0f;
+  return fmaxf(fabsf(x), -1.0f);  // maxNum: |x|, or -1 for a NaN (one FMNMX)
 }
 
 __device__ __forceinline__ void acc_pair(float a0, float a1, float g, float2& sum, float2& cnt) {
@@ -175,6 +177,125 @@ __global__ void __launch_bounds__(THREADS)
     if (!PREFETCH) load_row(row + gridDim.x);
   }
   if (tid == 0 && my_mask) atomicOr(notclose, my_mask);
+}
+
+// ------------------------------------------------------------------ rows, one warp per row
+// Rows of 513..4096 floats: a warp keeps its whole row in registers (NV float4 per lane), so an
+// iteration has no barrier and no shared-memory exchange, only the xor-shuffle fold, and the
+// fixed per-iteration cost (fold + update, ~60 issue slots) is spread over up to 128 elements per
+// lane instead of 64.  Rows arrive by 1-D bulk copies (cp.async.bulk, one mbarrier per warp): the
+// warp drains its buffer into registers and lane 0 immediately queues the NEXT row into the same
+// buffer, so HBM latency hides behind the ten iterations without a second register set.  Four
+// independent accumulator pairs keep the packed-fp32 pipe from waiting on one FFMA2 chain.
+template <int NV>
+struct WarpRowsCfg {
+  static constexpr int kWarps = 4;
+  static constexpr int kMinBlocks = NV >= 32 ? 3 : NV >= 24 ? 4 : NV >= 16 ? 5 : 8;
+};
+
+template <int NV, bool FULL>
+__global__ void __launch_bounds__(WarpRowsCfg<NV>::kWarps * 32, WarpRowsCfg<NV>::kMinBlocks)
+    octav_rows_warp(const float* __restrict__ x, long long rows, int cols, OctavConst k, int iters,
+                    float* __restrict__ trace, unsigned* __restrict__ notclose) {
+  constexpr int W = WarpRowsCfg<NV>::kWarps;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) uint64_t s_bar[W];
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int nvec = cols >> 2;  // FULL: nvec == NV * 32, no guards
+  const uint32_t row_bytes = static_cast<uint32_t>(cols) * 4u;
+  float4* buf = reinterpret_cast<float4*>(s_raw + static_cast<size_t>(warp) * row_bytes);
+  uint64_t* bar = &s_bar[warp];
+  const long long stride = static_cast<long long>(gridDim.x) * W;
+  long long row = static_cast<long long>(blockIdx.x) * W + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (row < rows) {
+      mbar_arrive_expect_tx(bar, row_bytes);
+      bulk_g2s(buf, x + row * cols, row_bytes, bar);
+    }
+  }
+  __syncwarp();
+  unsigned my_mask = 0, parity = 0;
+  for (; row < rows; row += stride) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    float4 a[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = j * 32 + lane;
+      float4 v;
+      if (FULL) v = buf[i];
+      else v = i < nvec ? buf[i] : make_float4(NAN, NAN, NAN, NAN);
+      // a = |x|, or -1 for a NaN (maxNum, one FMNMX): no guess >= 0 selects it
+      a[j].x = fmaxf(fabsf(v.x), -1.0f); a[j].y = fmaxf(fabsf(v.y), -1.0f);
+      a[j].z = fmaxf(fabsf(v.z), -1.0f); a[j].w = fmaxf(fabsf(v.w), -1.0f);
+    }
+    __syncwarp();  // every lane has read the buffer: the next row may land in it
+    if (lane == 0 && row + stride < rows) {
+      mbar_arrive_expect_tx(bar, row_bytes);
+      bulk_g2s(buf, x + (row + stride) * cols, row_bytes, bar);
+    }
+
+    float g = 1.0f;
+    int it = 0;
+    for (; it < iters; ++it) {
+      float2 s0 = make_float2(0.f, 0.f), s1 = s0, c0 = s0, c1 = s0;
+      if (g == g) {  // a NaN guess selects nothing
+        // Eight masks are formed before the four packed FMAs / adds that consume them: the
+        // compare runs on the half-rate ALU pipe with a longer latency than the FMA pipe, and a
+        // warp has at most three neighbours on its scheduler to hide that behind.
+#pragma unroll
+        for (int j = 0; j < NV; j += 2) {
+          const float2 m0 = make_float2(mask_ge(a[j].x, g), mask_ge(a[j].y, g));
+          const float2 m1 = make_float2(mask_ge(a[j].z, g), mask_ge(a[j].w, g));
+          const float2 m2 = make_float2(mask_ge(a[j + 1].x, g), mask_ge(a[j + 1].y, g));
+          const float2 m3 = make_float2(mask_ge(a[j + 1].z, g), mask_ge(a[j + 1].w, g));
+          s0 = __ffma2_rn(make_float2(a[j].x, a[j].y), m0, s0);
+          s1 = __ffma2_rn(make_float2(a[j].z, a[j].w), m1, s1);
+          c0 = __fadd2_rn(c0, m0);
+          c1 = __fadd2_rn(c1, m1);
+          s0 = __ffma2_rn(make_float2(a[j + 1].x, a[j + 1].y), m2, s0);
+          s1 = __ffma2_rn(make_float2(a[j + 1].z, a[j + 1].w), m3, s1);
+          c0 = __fadd2_rn(c0, m2);
+          c1 = __fadd2_rn(c1, m3);
+        }
+      }
+      if (g == 0.0f) {
+        // x >= 0 and x <= -0 both select a zero: zeros count twice at a zero guess (rare: once
+        // per row on ordinary weights, so they are counted here and not at load time)
+        float2 z0 = make_float2(0.f, 0.f), z1 = z0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          z0 = __fadd2_rn(z0, make_float2(a[j].x == 0.0f ? 1.0f : 0.0f, a[j].y == 0.0f ? 1.0f : 0.0f));
+          z1 = __fadd2_rn(z1, make_float2(a[j].z == 0.0f ? 1.0f : 0.0f, a[j].w == 0.0f ? 1.0f : 0.0f));
+        }
+        c0 = __fadd2_rn(c0, __fadd2_rn(z0, z1));
+      }
+      const float2 sa = __fadd2_rn(s0, s1), ca = __fadd2_rn(c0, c1);
+      float ts = sa.x + sa.y;
+      const int tc_lane = static_cast<int>(ca.x + ca.y);  // exact: <= 8 * NV
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      const int cnt_i = __reduce_add_sync(0xffffffffu, tc_lane);
+      const float ng = octav_update(ts, cnt_i, k);
+      if (lane == 0) {
+        trace[static_cast<long long>(it) * rows + row] = ng;
+        if (!is_close(g, ng)) my_mask |= 1u << it;
+      }
+      const bool fixed = (ng == g) || (ng != ng && g != g);
+      g = ng;
+      if (fixed) { ++it; break; }  // warp-uniform: every lane holds the same g
+    }
+    if (lane == 0) {
+      const bool self_close = is_close(g, g);
+      for (int r = it; r < iters; ++r) {
+        trace[static_cast<long long>(r) * rows + row] = g;
+        if (!self_close) my_mask |= 1u << r;
+      }
+    }
+  }
+  if (lane == 0 && my_mask) atomicOr(notclose, my_mask);
 }
 
 // Any cols / alignment (and the per-tensor case: rows == 1): the row is re-read
@@ -450,6 +571,40 @@ void launch_rows_nv(const float* x, long long rows, int cols, const OctavConst& 
                                                                              trace, notclose);
 }
 
+template <int NV, bool FULL>
+cudaError_t launch_rows_warp_k(const float* x, long long rows, int cols, const OctavConst& k,
+                               int iters, float* trace, unsigned* notclose, int sm_count,
+                               cudaStream_t st) {
+  constexpr int W = WarpRowsCfg<NV>::kWarps;
+  const size_t smem = static_cast<size_t>(W) * static_cast<size_t>(cols) * 4;
+  static bool configured = false;  // per instantiation; the attribute is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(octav_rows_warp<NV, FULL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, W * NV * 512);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octav_rows_warp<NV, FULL>,
+                                                                W * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sm_count) * per_sm;
+  const long long need = (rows + W - 1) / W;
+  if (grid > need) grid = need;
+  octav_rows_warp<NV, FULL><<<static_cast<unsigned>(grid), W * 32, smem, st>>>(
+      x, rows, cols, k, iters, trace, notclose);
+  return cudaSuccess;
+}
+
+template <int NV>
+cudaError_t launch_rows_warp(const float* x, long long rows, int cols, const OctavConst& k,
+                             int iters, float* trace, unsigned* notclose, int sm_count,
+                             cudaStream_t st) {
+  if (cols == NV * 128) return launch_rows_warp_k<NV, true>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
+  return launch_rows_warp_k<NV, false>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
+}
+
 }  // namespace
 
 size_t octav_workspace_bytes(long long groups, int iters) {
@@ -488,7 +643,16 @@ cudaError_t launch_octav_rows(const float* x, long long rows, long long cols, in
   if (vec) {
     const int c = static_cast<int>(cols);
     const int v4 = c / 4;  // float4 per row; <= 8 per thread, thread count grows with the row
+    static const bool cta_rows = getenv("AEQB_OCTAV_CTA_ROWS") != nullptr;  // A/B runs
+    cudaError_t le = cudaSuccess;
     if (v4 <= 128) launch_rows_nv<1, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+    else if (v4 <= 1024 && !cta_rows) {  // 513..4096 floats: one warp per row, row in registers
+      if (v4 <= 256) le = launch_rows_warp<8>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+      else if (v4 <= 512) le = launch_rows_warp<16>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+      else if (v4 <= 768) le = launch_rows_warp<24>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+      else le = launch_rows_warp<32>(x, rows, c, k, iters, trace, notclose, sm_count, st);
+      if (le != cudaSuccess) return le;
+    }
     else if (v4 <= 256) launch_rows_nv<2, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else if (v4 <= 512) launch_rows_nv<4, 128>(x, rows, c, k, iters, trace, notclose, sm_count, st);
     else if (v4 <= 1024) launch_rows_nv<16, 64>(x, rows, c, k, iters, trace, notclose, sm_count, st);

@@ -78,7 +78,8 @@ def test_octav_golden(cuda):
     np.testing.assert_allclose(clip, z[key + "_clip"], rtol=1e-6, atol=1e-12)
 
 
-@pytest.mark.parametrize("shape", [(64, 4096), (24, 11008), (5, 16384), (9, 260), (3, 33), (40, 1024)])
+@pytest.mark.parametrize("shape", [(64, 4096), (24, 11008), (5, 16384), (9, 260), (3, 33), (40, 1024),
+                                   (33, 2048), (17, 3072), (11, 3584), (13, 1536), (19, 640), (1, 4096)])
 @pytest.mark.parametrize("bits", [4, 8])
 def test_octav_rows_vs_oracle(cuda, shape, bits):
   """Row-resident kernel (every NV class), the generic kernel (odd shapes) and the trace /
@@ -101,6 +102,26 @@ def test_octav_rows_vs_oracle(cuda, shape, bits):
   got10 = device.octav_clip_rows(x, bits, early_stop=False).cpu().numpy()
   np.testing.assert_allclose(got10, want10, rtol=1e-6, atol=1e-12)
   assert len(trace) <= 10
+
+
+@pytest.mark.parametrize("shape", [(3700, 2048), (2000, 4096)])
+def test_octav_rows_warp_pipeline(cuda, shape):
+  """More rows than resident warps: every warp of the one-warp-per-row kernel refills its
+  shared-memory row buffer (bulk copy + mbarrier phase flip) at least once; rows with NaN / inf
+  / zero elements sit in both rounds."""
+  from aeq_b200 import device
+  import torch
+  w = O.synthetic_weight(*shape, index=91)
+  for r in (0, shape[0] - 1):
+    w[r, 5] = np.nan
+    w[r, 77] = 0.0
+  w[1, :] = 0.0
+  w[shape[0] - 2, ::2] = 0.0
+  w[shape[0] - 3, 9] = np.inf
+  with np.errstate(all="ignore"):
+    want = O.octav_clip(w, 4, (1,))
+  got = device.octav_clip_rows(torch.from_numpy(w).to(cuda), 4).cpu().numpy()
+  np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.parametrize("shape,block", [((64, 4096), 32), ((7, 11008), 32), ((16, 1024), 64),
@@ -237,9 +258,14 @@ def test_hadamard_reference_literals(cuda):
 
 @pytest.mark.parametrize("shape,n", [((64, 4096), 4096), ((16, 4096), 128), ((8, 11008), 256),
                                      ((4, 16384), 16384), ((3, 8192), 8192), ((5, 2048), 2),
-                                     ((2, 32768), 32768), ((6, 24), 8)])
+                                     ((2, 32768), 32768), ((6, 24), 8),
+                                     # 16 KiB tile kernel (numel % 4096 == 0, n = 256..4096), the
+                                     # last one with more tiles than resident warps
+                                     ((16, 11008), 256), ((24, 1024), 512), ((8, 4096), 1024),
+                                     ((4, 3072), 1024), ((32, 2048), 2048), ((1200, 4096), 4096)])
 def test_hadamard_rows_vs_oracle(cuda, shape, n):
-  """Every radix path (even / odd log2 n), tiled segments, and the > 64 KiB global fallback."""
+  """Every radix path (even / odd log2 n), tiled segments, the 16 KiB tile kernel and the
+  > 64 KiB global fallback."""
   from aeq_b200 import device
   import torch
   w = O.synthetic_weight(*shape, index=n % 89)
