@@ -38,11 +38,25 @@ struct OctavConst {
   float s;         // f32(4^-bits / divisor)
   float one_m_s;   // 1.0f - s   (fp32, octav.py:105)
   double s_n;      // double(s) * N (octav.py:106, float64 because N is np.int64)
+  float s_n_f32;   // s_n when it is an fp32 value (N a power of two, ...), else NaN
 };
 
+// den = f32(f64(den0) + s_n).  When s_n is itself an fp32 value and both terms sit within 29
+// binary orders of each other (make_const checks the range of N and s), the float64 sum of two
+// fp32 values is exact, so rounding it to fp32 is the correctly rounded fp32 sum: one FADD
+// instead of F2F.F64 + DADD + F2F.F32.  Same bits either way.
 __device__ __forceinline__ float octav_update(float num, int cnt, const OctavConst& k) {
   const float den0 = __fmul_rn(static_cast<float>(cnt), k.one_m_s);
-  const float den = static_cast<float>(static_cast<double>(den0) + k.s_n);
+  const float den = (k.s_n_f32 == k.s_n_f32) ? __fadd_rn(den0, k.s_n_f32)
+                                             : static_cast<float>(static_cast<double>(den0) + k.s_n);
+  return __fdiv_rn(num, den);
+}
+
+// Same with the count already an exact fp32 integer (< 2^24): no F2I / I2F round trip.
+__device__ __forceinline__ float octav_update_f(float num, float cnt, const OctavConst& k) {
+  const float den0 = __fmul_rn(cnt, k.one_m_s);
+  const float den = (k.s_n_f32 == k.s_n_f32) ? __fadd_rn(den0, k.s_n_f32)
+                                             : static_cast<float>(static_cast<double>(den0) + k.s_n);
   return __fdiv_rn(num, den);
 }
 
@@ -392,12 +406,10 @@ __global__ void __launch_bounds__(256)
     }
     __syncwarp();
     float a[32];
-    int zeros = 0;
+    // a = |x|, or -1 for a NaN (maxNum, one FMNMX): no guess >= 0 selects it
 #pragma unroll
-    for (int p = 0; p < 32; ++p) a[p] = condition(t[lane * 33 + p], zeros);
+    for (int p = 0; p < 32; ++p) a[p] = fmaxf(fabsf(t[lane * 33 + p]), -1.0f);
     __syncwarp();
-#pragma unroll
-    for (int o = 1; o < LPB; o <<= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
     const long long seg_e = e0 + 32LL * lane;    // first element of this lane's segment
     const bool valid = seg_e < n;
     const long long blk = seg_e / BLOCK;
@@ -411,14 +423,22 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int p = 0; p < 32; p += 2) acc_pair(a[p], a[p + 1], g, sum, cnt);
       }
+      if (__any_sync(0xffffffffu, g == 0.0f)) {
+        // x >= 0 and x <= -0 both select a zero: at a zero guess the zeros count twice.  Rare
+        // (one iteration per block on ordinary weights), so they are counted here, not at load.
+        float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 32; p += 2)
+          z = __fadd2_rn(z, make_float2(a[p] == 0.0f ? 1.0f : 0.0f, a[p + 1] == 0.0f ? 1.0f : 0.0f));
+        if (g == 0.0f) cnt = __fadd2_rn(cnt, z);
+      }
       float ts = sum.x + sum.y, tc = cnt.x + cnt.y;
 #pragma unroll
       for (int o = 1; o < LPB; o <<= 1) {
         ts += __shfl_xor_sync(0xffffffffu, ts, o);
         tc += __shfl_xor_sync(0xffffffffu, tc, o);
       }
-      const int cnt_i = static_cast<int>(tc) + (g == 0.0f ? zeros : 0);
-      const float ng = octav_update(ts, cnt_i, k);
+      const float ng = octav_update_f(ts, tc, k);
       if (writer) {
         trace[static_cast<long long>(it) * nblk + blk] = ng;
         if (!is_close(g, ng)) my_mask |= 1u << it;
@@ -556,6 +576,13 @@ OctavConst make_const(int bits, float divisor, long long n) {
   k.s = static_cast<float>(p / static_cast<double>(divisor));
   k.one_m_s = 1.0f - k.s;
   k.s_n = static_cast<double>(k.s) * static_cast<double>(n);
+  // fp32 shortcut of octav_update: s_n exact in fp32, and |log2(den0 / s_n)| <= 29 for every
+  // count 1..n (den0 in [1 - s, n], s_n = s * n, s >= 2^-18 for bits <= 8, n <= 2^24: the two
+  // ratios are bounded by 1 / s and s * n < 2^24); den0 == 0 adds exactly.
+  const float f = static_cast<float>(k.s_n);
+  const bool exact = static_cast<double>(f) == k.s_n && bits >= 1 && bits <= 8 && divisor >= 1.0f &&
+                     divisor <= 64.0f && n >= 1 && n <= (1LL << 24);
+  k.s_n_f32 = exact ? f : NAN;
   return k;
 }
 
