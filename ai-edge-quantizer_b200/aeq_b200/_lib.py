@@ -39,6 +39,11 @@ SIGNATURES = {
     "aeqb_requant_blocks_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "aeqb_requant_rows_batch_f32": (_I, [_P, _L, _I, _I, _P]),
     "aeqb_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I, _P]),
+    "aeqb_requant_rows_batch_mirror_f32": (_I, [_P, _L, _I, _I, _P, _I, _P]),
+    "aeqb_peer_alloc": (_I, [_c.c_size_t, _P, _P]),
+    "aeqb_peer_open": (_I, [_P, _P]),
+    "aeqb_peer_close": (_I, [_P]),
+    "aeqb_peer_free": (_I, [_P]),
     "aeqb_minmax_workspace_bytes": (_c.c_size_t, []),
     "aeqb_minmax_tensors_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P]),
     "aeqb_minmax_tensor_f32": (_I, [_P, _L, _F, _F, _I, _I, _P, _P, _P]),

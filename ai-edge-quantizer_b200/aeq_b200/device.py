@@ -244,11 +244,13 @@ def pack_bits(q: torch.Tensor, bits: int) -> torch.Tensor:
 
 # ------------------------------------------------------------------ batched (whole model)
 def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = True,
-                       want_packed: bool = False, outs=None):
+                       want_packed: bool = False, outs=None, mirror=None):
   """Per-channel requantisation of many tensors in as few persistent launches as possible.
 
   Returns a list of Requantized.  `outs` may carry preallocated outputs from a previous call
-  (same shapes) to keep the loop allocation-free.
+  (same shapes) to keep the loop allocation-free.  `mirror` (peer.PeerScales): the scale outputs
+  in `outs` are views into `mirror.local`, and the kernel also stores every scale into the other
+  ranks' copies of the gathered buffer (aeqb_requant_rows_batch_mirror_f32).
   """
   import ctypes
   n = len(xs)
@@ -267,6 +269,10 @@ def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = Tru
   for i, (x, o) in enumerate(zip(xs, outs)):
     jobs[i] = _lib.RowsJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
                            _ptr(o.scale), _ptr(o.zero_point))
+  if mirror is not None:
+    _lib.call("aeqb_requant_rows_batch_mirror_f32", ctypes.cast(jobs, ctypes.c_void_p), n, bits,
+              int(symmetric), mirror.deltas_ptr, mirror.n_peers, _stream())
+    return outs
   _lib.call("aeqb_requant_rows_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), n, bits,
             int(symmetric), _stream())
   return outs

@@ -4,6 +4,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <cstring>
 #include <vector>
 
 #include "../../include/aeqb200.h"
@@ -69,11 +70,19 @@ struct RowsOpts { int bits, symmetric; };
 
 // Runs every job: stream-class jobs are grouped into <= kMaxInlineJobs batches per
 // class (one persistent launch each), the rest go through the generic kernel.
-int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who) {
+int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who,
+             const aeqb::PeerMirror* peers = nullptr) {
   const int sms = sm_count();
+  if (peers && peers->n > 0) {  // only the tile-stream kernels mirror their scales
+    for (int64_t i = 0; i < n; ++i)
+      if (jobs[i].rows > 0 && jobs[i].cols > 0 && aeqb::rows_job_class(jobs[i], o.bits) == 0)
+        return fail("%s: tensor %lld ([%lld, %d]) does not take the tile-stream kernel; gather its "
+                    "scales with a collective", who, (long long)i, (long long)jobs[i].rows, jobs[i].cols);
+  }
   for (int klass = 1; klass <= 4; ++klass) {
     aeqb::RowsBatch b{};
     b.bits = o.bits; b.symmetric = o.symmetric;
+    if (peers) b.peers = *peers;
     auto flush = [&]() -> int {
       if (b.n_jobs == 0) return 0;
       int rc = check(aeqb::launch_requant_rows_stream(b, klass, sms, st), who);
@@ -184,6 +193,57 @@ int aeqb_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int b
   return run_rows(v.data(), n_jobs, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
                   "aeqb_requant_rows_batch_f32");
 }
+
+int aeqb_requant_rows_batch_mirror_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
+                                       int symmetric, const int64_t* peer_delta_bytes, int n_peers,
+                                       void* stream) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad job list");
+  if (n_peers < 0 || n_peers > aeqb::kMaxPeers || (n_peers > 0 && !peer_delta_bytes))
+    return fail("bad peer list (0..%d peers)", aeqb::kMaxPeers);
+  aeqb::PeerMirror pm{};
+  pm.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) {
+    if (peer_delta_bytes[i] % 4) return fail("peer offset %d is not a multiple of 4 bytes", i);
+    pm.delta[i] = peer_delta_bytes[i];
+  }
+  std::vector<aeqb::RowsJob> v(static_cast<size_t>(n_jobs));
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const aeqb_rows_job& a = jobs[i];
+    if (int rc = rows_args_ok(a.rows, a.cols, bits, a.packed, a.x)) return rc;
+    if (n_peers > 0 && !a.scale) return fail("job %lld has no scale output to mirror", (long long)i);
+    aeqb::RowsJob j{};
+    j.x = a.x; j.q = a.q; j.packed = a.packed; j.scale = a.scale; j.zp = a.zp; j.clip = a.clip;
+    j.rows = a.rows; j.cols = static_cast<int>(a.cols);
+    j.mm_stride = 1; j.clip_stride = 1; j.out_stride = 1;
+    v[static_cast<size_t>(i)] = j;
+  }
+  return run_rows(v.data(), n_jobs, {bits, symmetric ? 1 : 0}, static_cast<cudaStream_t>(stream),
+                  "aeqb_requant_rows_batch_mirror_f32", &pm);
+}
+
+// ---- peer-visible device buffers (CUDA IPC): the gathered scale buffer every rank maps
+int aeqb_peer_alloc(size_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail("aeqb_peer_alloc: bad arguments");
+  void* p = nullptr;
+  if (int rc = check(cudaMalloc(&p, bytes), "aeqb_peer_alloc")) return rc;
+  if (int rc = check(cudaMemset(p, 0, bytes), "aeqb_peer_alloc")) { cudaFree(p); return rc; }
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+  if (int rc = check(cudaIpcGetMemHandle(&h, p), "aeqb_peer_alloc")) { cudaFree(p); return rc; }
+  std::memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return 0;
+}
+
+int aeqb_peer_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail("aeqb_peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  return check(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "aeqb_peer_open");
+}
+
+int aeqb_peer_close(void* ptr) { return check(cudaIpcCloseMemHandle(ptr), "aeqb_peer_close"); }
+int aeqb_peer_free(void* ptr) { return check(cudaFree(ptr), "aeqb_peer_free"); }
 
 int aeqb_requant_given_minmax_f32(const float* x, int64_t rows, int64_t cols, int bits,
                                   int symmetric, const float* mn, const float* mx,

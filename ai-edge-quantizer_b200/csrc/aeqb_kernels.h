@@ -41,12 +41,23 @@ struct RowsJob {
   int out_stride;
   long long tile0, tile_end;    // this job's tile range inside the batch (launcher)
 };
+// Scales (and zero points) of a sharded job set can be mirrored into the other ranks' copies of
+// the gathered buffer from the kernel's own epilogue: the lane that publishes a row's scale also
+// stores it at the same offset of up to kMaxPeers peer mappings (NVLink peer memory), which is the
+// all-gather of per-channel scales without a collective launch.  delta[i] = peer base - local
+// base in bytes; the local `scale` pointers must point into the local copy of that buffer.
+constexpr int kMaxPeers = 15;
+struct PeerMirror {
+  int n;
+  long long delta[kMaxPeers];
+};
 struct RowsBatch {
   RowsJob jobs[kMaxInlineJobs];
   int n_jobs;
   int bits;
   int symmetric;
   long long n_tiles;
+  PeerMirror peers;
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
 int rows_job_class(const RowsJob& j, int bits);

@@ -64,8 +64,15 @@ __device__ __forceinline__ void acc_reset(RowAcc& a) {
 
 // uqt:492-586 for one row.  `xmax` bounds |x| over the row (for the divide
 // window); pass +inf when the row was not scanned.
+__device__ __forceinline__ void publish_scale(float* p, float v, const PeerMirror& pm) {
+  *p = v;
+  for (int i = 0; i < pm.n; ++i)  // peer copies of the gathered scale buffer (NVLink stores)
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(p) + pm.delta[i]) = v;
+}
+
 __device__ __forceinline__ RowQ finalize_row(const RowsJob& a, int bits, bool sym, long long row,
-                                            float mn, float mx, float xmax, bool publish) {
+                                            float mn, float mx, float xmax, bool publish,
+                                            const PeerMirror& pm) {
   const QRange qr = qrange(bits, sym);
   float scale, zpf = 0.0f;
   if (a.given_scale) {  // uniform_quantize (uqt:273-362) with the caller's parameters, no statistics
@@ -99,7 +106,7 @@ __device__ __forceinline__ RowQ finalize_row(const RowsJob& a, int bits, bool sy
   // without clipping, i.e. it wraps; identity unless a clip shrank the range.
   const int zpi = static_cast<int>(static_cast<int8_t>(rni(zpf)));
   if (publish) {
-    if (a.scale) a.scale[row * a.out_stride] = scale;
+    if (a.scale) publish_scale(&a.scale[row * a.out_stride], scale, pm);
     if (a.zp) a.zp[row * a.out_stride] = zpi;
   }
   RowQ r;
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         mine.b = sc; mine.y = dv.y; mine.zp = 0.0f;
         mine.mode = dv.fast ? kFastClamp : kSlow;
         if (my_c == r * cpr) {
-          if (jcopy.scale) jcopy.scale[grow * jcopy.out_stride] = sc;
+          if (jcopy.scale) publish_scale(&jcopy.scale[grow * jcopy.out_stride], sc, b.peers);
           if (jcopy.zp) jcopy.zp[grow * jcopy.out_stride] = 0;
         }
       } else {
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
         mx = acc.nan ? NAN : ord2f(acc.mx_ord);
         xmax = max_nan(fabsf(mn), fabsf(mx));
       }
-      mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c == r * cpr);
+      mine = finalize_row(jcopy, bits, sym, grow, mn, mx, xmax, my_c == r * cpr, b.peers);
       }
     }
     // Buffer (it+2)%3 was last read during the previous tile, which every warp has
@@ -524,7 +531,9 @@ __global__ void __launch_bounds__(256)
     mx = warp_max_nan(mx);
     xmax = max_nan(fabsf(mn), fabsf(mx));
   }
-  RowQ rq = finalize_row(a, bits, sym, row, mn, mx, xmax, lane == 0);
+  PeerMirror none;
+  none.n = 0;
+  RowQ rq = finalize_row(a, bits, sym, row, mn, mx, xmax, lane == 0, none);
   rq.mode = kSlow;
   const int per = a.packed ? 8 / bits : 1;  // elements per packed byte
   for (int c0 = lane * per; c0 < a.cols; c0 += 32 * per) {

@@ -548,8 +548,19 @@ def main():
 
   state = {}
   # Per-channel scales of this rank's tensors live in ONE flat buffer (each tensor's scale output
-  # is a view into it), so the path's single collective needs no packing step.
-  flat_scales = torch.empty(T * ROWS, dtype=torch.float32, device=dev)
+  # is a view into it), so the path's single exchange needs no packing step.  At N > 1 that
+  # buffer is this rank's row of a [world, T * ROWS] buffer every rank maps (aeq_b200/peer.py):
+  # the requantisation kernel stores each row's scale into every peer's copy from its own
+  # epilogue, so the all-gather of scales costs no launch.  If peer mapping is not available on
+  # the box (or AEQB_BENCH_NCCL_GATHER is set) the exchange is one NCCL all-gather per step.
+  mirror, mirror_note = None, None
+  if world > 1 and not os.environ.get("AEQB_BENCH_NCCL_GATHER"):
+    try:
+      from aeq_b200 import peer
+      mirror = peer.PeerScales(T * ROWS, dev)
+    except Exception as e:  # pylint: disable=broad-except
+      mirror, mirror_note = None, f"{type(e).__name__}: {e}"[:200]
+  flat_scales = mirror.local if mirror is not None else torch.empty(T * ROWS, dtype=torch.float32, device=dev)
   gathered = (torch.empty(world * T * ROWS, dtype=torch.float32, device=dev) if world > 1 else None)
   state["r8"] = [device.Requantized(
       torch.empty((ROWS, COLS), dtype=torch.int8, device=dev), None,
@@ -557,6 +568,9 @@ def main():
       torch.empty((ROWS, 1), dtype=torch.int32, device=dev)) for i in range(T)]
 
   def step_int8():
+    if mirror is not None:  # scales reach every rank's gathered buffer from inside the kernel
+      device.requant_rows_batch(ws, 8, True, outs=state["r8"], mirror=mirror)
+      return
     device.requant_rows_batch(ws, 8, True, outs=state["r8"])
     if world > 1:  # the path's one collective: all ranks learn every per-channel scale
       dist.all_gather_into_tensor(gathered, flat_scales)
@@ -587,6 +601,13 @@ def main():
   if rank == 0:
     sampler.start()
   ms8, launches8 = timed(step_int8, a.steps, max(a.warmup, 3))
+  exchange_ok = None
+  if mirror is not None:  # the in-kernel exchange against NCCL's all-gather of the same scales
+    mirror.sync()
+    dist.all_gather_into_tensor(gathered, flat_scales)
+    okt = torch.tensor([int(torch.equal(gathered.view(world, -1), mirror.gathered))], device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    exchange_ok = bool(okt.item())
   ms4, launches4 = timed(step_int4, a.steps, max(a.warmup, 3))
   clocks = sampler.stop() if rank == 0 else None
   value8 = world * n_bytes / ms8 / 1e6
@@ -697,7 +718,11 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(T), "tensors_per_gpu": T, "shape": [ROWS, COLS],
                    "l2": "inputs are 4 GiB per GPU per step, >> 126 MB L2: no flush needed",
-                   "collective": "one NCCL all-gather of per-channel scales per step" if world > 1 else "none (N=1)",
+                   "collective": ("none (N=1)" if world == 1 else
+                                  "per-channel scales stored into every peer's gathered buffer by the requantisation kernel itself (NVLink peer memory, aeqb_requant_rows_batch_mirror_f32); no collective launch" if mirror is not None else
+                                  "one NCCL all-gather of per-channel scales per step"),
+                   "scale_exchange_matches_nccl_all_gather": exchange_ok,
+                   "peer_mapping_error": mirror_note,
                    "sharding": "tensors partitioned across ranks, no data-path collective"},
         "modes": {
             "int8_perchannel": {"value": value8, "ms_per_step": ms8, "launches_per_step": launches8 / a.steps},
@@ -718,6 +743,8 @@ def main():
         "gpu_launches": int(launches8),
         "clocks": clocks,
     }))
+  if mirror is not None:
+    mirror.close()
   if world > 1:
     dist.destroy_process_group()
 

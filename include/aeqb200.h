@@ -113,6 +113,25 @@ AEQB_API int aeqb_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jo
 AEQB_API int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block,
                                            int bits, void* stream);
 
+/* ---------------------------------------------------------------- weights, batched + sharded
+ * The sharded form of the call above (one process per GPU, tensors partitioned across ranks): the
+ * reference gathers every tensor's quantisation parameters in one process
+ * (params_generator.py:110-183 fills a single dict); here each rank's kernel also stores every
+ * row's scale at the same offset of `n_peers` peer mappings of the gathered scale buffer (NVLink
+ * peer memory), so the all-gather of per-channel scales needs no collective launch.
+ * `peer_delta_bytes[i]` = peer i's base address of that buffer minus the local base address; the
+ * jobs' `scale` pointers must point into the local copy.  Remote copies are complete once the
+ * writer's stream has been synchronised and the ranks have met (a barrier). */
+AEQB_API int aeqb_requant_rows_batch_mirror_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
+                                                int symmetric, const int64_t* peer_delta_bytes,
+                                                int n_peers, void* stream);
+/* A device buffer other processes on the node can map (CUDA IPC): `handle64` receives 64 opaque
+ * bytes to send to the peers, which call aeqb_peer_open on them. */
+AEQB_API int aeqb_peer_alloc(size_t bytes, void** ptr, void* handle64);
+AEQB_API int aeqb_peer_open(const void* handle64, void** ptr);
+AEQB_API int aeqb_peer_close(void* ptr);
+AEQB_API int aeqb_peer_free(void* ptr);
+
 /* ---------------------------------------------------------------- host buffers
  * The call a NumPy caller makes (naive_min_max_quantize.get_tensor_quant_params,
  * :34-110, over every weight of a model): HOST pointers in the job structs, in

@@ -141,3 +141,55 @@ def test_full_size_properties(cuda):
   sc = b.scale.repeat_interleave(32, dim=1)
   assert bool(((b.q.float() * sc - x).abs() <= sc * 0.50005).all())
   assert bool((b.scale_f16.float() == b.scale).all())
+
+
+@pytest.mark.gpu
+def test_scales_mirrored_into_peer_copies(cuda):
+  """aeqb_requant_rows_batch_mirror_f32: the kernel stores every row's scale at the same offset
+  of each peer mapping of the gathered buffer.  Here the "peers" are two more rows of one local
+  buffer (the kernel only sees byte offsets); the cross-process mapping itself is exercised by
+  bench.py at N > 1, which compares it with NCCL's all-gather of the same scales."""
+  import ctypes
+  import types
+  import torch
+  from aeq_b200 import _lib, device
+  shapes = [(64, 4096), (24, 11008), (40, 1024), (48, 2560)]   # every tile-stream class
+  ws = [O.synthetic_weight(r, c, index=60 + i) for i, (r, c) in enumerate(shapes)]
+  xs = [_dev(w, cuda) for w in ws]
+  slots = sum(r for r, _ in shapes)
+  buf = torch.full((3, slots), -1.0, dtype=torch.float32, device=cuda)
+  deltas = (ctypes.c_int64 * 2)(buf[1].data_ptr() - buf[0].data_ptr(), buf[2].data_ptr() - buf[0].data_ptr())
+  mirror = types.SimpleNamespace(deltas_ptr=ctypes.cast(deltas, ctypes.c_void_p), n_peers=2)
+  outs, off = [], 0
+  for r, c in shapes:
+    outs.append(device.Requantized(torch.empty((r, c), dtype=torch.int8, device=cuda), None,
+                                   buf[0, off:off + r].view(r, 1),
+                                   torch.empty((r, 1), dtype=torch.int32, device=cuda)))
+    off += r
+  device.requant_rows_batch(xs, 8, True, outs=outs, mirror=mirror)
+  torch.cuda.synchronize()
+  want = np.concatenate([O.minmax_requant(w, 8, True)["scale"].reshape(-1) for w in ws])
+  got = buf.cpu().numpy()
+  for k in range(3):
+    np.testing.assert_array_equal(got[k], want)
+  for w, o in zip(ws, outs):
+    np.testing.assert_array_equal(o.q.cpu().numpy(), O.minmax_requant(w, 8, True)["q"])
+  # a tensor that falls to the generic kernel cannot be mirrored: loud error, nothing written
+  odd = _dev(O.synthetic_weight(5, 33, index=3), cuda)
+  o = device.Requantized(torch.empty((5, 33), dtype=torch.int8, device=cuda), None,
+                         buf[0, :5].view(5, 1), torch.empty((5, 1), dtype=torch.int32, device=cuda))
+  with pytest.raises(_lib.AeqbError, match="tile-stream"):
+    device.requant_rows_batch([odd], 8, True, outs=[o], mirror=mirror)
+
+
+@pytest.mark.gpu
+def test_peer_buffer_alloc_free(cuda):
+  """aeqb_peer_alloc hands out a zeroed device buffer and a 64-byte IPC handle."""
+  import ctypes
+  from aeq_b200 import _lib
+  ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+  _lib.call("aeqb_peer_alloc", 1 << 20, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
+  assert ptr.value and any(bytes(handle))
+  _lib.call("aeqb_peer_free", ptr)
+  with pytest.raises(_lib.AeqbError):
+    _lib.call("aeqb_peer_alloc", 0, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
