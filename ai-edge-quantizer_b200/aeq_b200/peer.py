@@ -94,7 +94,7 @@ class PeerScales:
         pass
     self._peer_ptrs = []
     if self._base is not None:
-      torch.cuda.synchronize(self.device)
+      self._device_sync()
       dist.barrier(group=self.group)
       _lib.call("aeqb_peer_free", self._base)
       self._base = None
@@ -109,8 +109,12 @@ class PeerScales:
 
   def sync(self):
     """After this, every rank's `gathered` holds all rows written before the call."""
-    torch.cuda.synchronize(self.device)
+    self._device_sync()
     dist.barrier(group=self.group)
+
+  def _device_sync(self):
+    if self.device.type == "cuda":
+      torch.cuda.synchronize(self.device)
 
   def close(self):
     if self._base is None:

@@ -92,3 +92,50 @@ def test_allgather_validates_ownership():
     sharding.allgather_vectors({1: torch.zeros(3)}, [3, 3], [0, 0])
   with pytest.raises(ValueError, match="expected 3 values"):
     sharding.allgather_vectors({0: torch.zeros(2)}, [3], [0])
+
+
+def _peer_worker(rank, world, port, out_dir, fake_success_on):
+  """PeerScales set-up on a box without CUDA: the allocation fails (really, or not at all on the
+  rank that fakes it) and every rank must leave the constructor with the same RuntimeError."""
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from aeq_b200 import _lib, peer
+    calls = []
+    if rank in fake_success_on:
+      real = _lib.call
+
+      def fake(name, *args):
+        calls.append(name)
+        if name == "aeqb_peer_alloc":
+          args[1]._obj.value = 0x10000  # ctypes.byref(ptr)
+          return None
+        if name == "aeqb_peer_free":
+          return None
+        return real(name, *args)
+      peer._lib.call = fake
+    try:
+      peer.PeerScales(16, torch.device("cpu"))
+      outcome = "constructed"
+    except RuntimeError as e:
+      outcome = str(e)
+    with open(os.path.join(out_dir, f"peer{rank}.txt"), "w") as f:
+      f.write(outcome + "\n" + ",".join(calls))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fake_success_on", [(), (1,)])
+def test_world2_peer_setup_fails_together(tmp_path, fake_success_on):
+  """A rank whose peer-visible allocation fails must not leave the others in a collective: the
+  vote makes every rank raise (and the rank that did allocate frees its buffer)."""
+  if torch.cuda.is_available():
+    pytest.skip("the failure path needs a box without CUDA")
+  port = _free_port()
+  mp.start_processes(_peer_worker, args=(2, port, str(tmp_path), fake_success_on), nprocs=2,
+                     join=True, start_method="spawn")
+  for r in range(2):
+    outcome, calls = (tmp_path / f"peer{r}.txt").read_text().split("\n")
+    assert "allocating the peer-visible buffer failed on at least one rank" in outcome
+    if r in fake_success_on:
+      assert calls.split(",") == ["aeqb_peer_alloc", "aeqb_peer_free"]
