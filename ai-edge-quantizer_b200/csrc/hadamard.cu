@@ -8,6 +8,11 @@
 // fp32 constant fl(1 / fl(sqrt(n))) the reference's matrix entries hold
 // (hadamard_rotation.py:79-89).  The kernel is HBM-bound: 4 B read + 4 B written.
 //
+// Three kernels, picked by shape in launch_hadamard_rows: `hadamard_tiles` (n = 256..4096 on
+// tensors that are whole 16 KiB tiles: one warp per tile, bulk copies in and out, packed-fp32
+// butterflies in registers — the hot shapes), `hadamard_rows_reg` (rows of 256-float groups, n up
+// to 8192) and the shared-memory butterfly below for everything else.
+//
 // Shared-memory butterfly: a CTA owns one row at a time (cols <= 16384 floats =
 // 64 KiB), loads it with 128-bit loads, runs radix-4 passes (two butterfly stages
 // per pass, each thread owns a 4-point group in registers, so shared memory is

@@ -8,7 +8,8 @@
 // and stops EARLY only when np.allclose(old, new) holds for every group of the
 // tensor at once (octav.py:109).  Groups never interact except through that stop
 // time, so this file computes every group's whole trajectory in ONE pass over HBM
-// with the group resident in registers (4 B read per weight, no re-reads), records
+// with the group resident in registers (4 B read per weight, no re-reads; rows of 513..4096
+// floats: one warp per row fed by bulk copies, `octav_rows_warp`), records
 // the trace [max_iterations, groups] plus a bit mask "some group was not yet
 // converged after iteration i", and a tiny second kernel picks the iteration the
 // reference would have stopped at.
