@@ -208,7 +208,7 @@ struct WarpRowsCfg {
   static constexpr int kMinBlocks = NV >= 32 ? 3 : NV >= 24 ? 4 : NV >= 16 ? 5 : 8;
 };
 
-template <int NV, bool FULL>
+template <int NV, bool FULL, bool SKIP>
 __global__ void __launch_bounds__(WarpRowsCfg<NV>::kWarps * 32, WarpRowsCfg<NV>::kMinBlocks)
     octav_rows_warp(const float* __restrict__ x, long long rows, int cols, OctavConst k, int iters,
                     float* __restrict__ trace, unsigned* __restrict__ notclose) {
@@ -251,17 +251,34 @@ __global__ void __launch_bounds__(WarpRowsCfg<NV>::kWarps * 32, WarpRowsCfg<NV>:
       mbar_arrive_expect_tx(bar, row_bytes);
       bulk_g2s(buf, x + (row + stride) * cols, row_bytes, bar);
     }
+    // SKIP: lane j remembers the largest magnitude of float4 slot j over the whole warp (128
+    // elements; REDUX.MAX on the bit patterns of non-negative floats).  An iteration then votes
+    // once which slots hold ANY element >= the guess and jumps over the others: they would add
+    // exactly +0 to both accumulators, so the result is bit-identical.  The guess climbs towards
+    // the tail of the row (1 -> 0 -> mean |x| -> ...): from the fourth or fifth iteration on only
+    // the slots with outliers are left, and the first iteration (guess 1) is usually empty.
+    float slot_max = 0.0f;
+    if (SKIP) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float m = fmaxf(fmaxf(fmaxf(a[j].x, a[j].y), fmaxf(a[j].z, a[j].w)), 0.0f);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if (lane == j) slot_max = __uint_as_float(wm);
+      }
+    }
 
     float g = 1.0f;
     int it = 0;
     for (; it < iters; ++it) {
       float2 s0 = make_float2(0.f, 0.f), s1 = s0, c0 = s0, c1 = s0;
+      const unsigned active = SKIP ? __ballot_sync(0xffffffffu, slot_max >= g) : 0xffffffffu;
       if (g == g) {  // a NaN guess selects nothing
         // Eight masks are formed before the four packed FMAs / adds that consume them: the
         // compare runs on the half-rate ALU pipe with a longer latency than the FMA pipe, and a
         // warp has at most three neighbours on its scheduler to hide that behind.
 #pragma unroll
         for (int j = 0; j < NV; j += 2) {
+          if (SKIP && !(active & (3u << j))) continue;  // warp-uniform
           const float2 m0 = make_float2(mask_ge(a[j].x, g), mask_ge(a[j].y, g));
           const float2 m1 = make_float2(mask_ge(a[j].z, g), mask_ge(a[j].w, g));
           const float2 m2 = make_float2(mask_ge(a[j + 1].x, g), mask_ge(a[j + 1].y, g));
@@ -599,7 +616,7 @@ void launch_rows_nv(const float* x, long long rows, int cols, const OctavConst& 
                                                                              trace, notclose);
 }
 
-template <int NV, bool FULL>
+template <int NV, bool FULL, bool SKIP>
 cudaError_t launch_rows_warp_k(const float* x, long long rows, int cols, const OctavConst& k,
                                int iters, float* trace, unsigned* notclose, int sm_count,
                                cudaStream_t st) {
@@ -607,20 +624,20 @@ cudaError_t launch_rows_warp_k(const float* x, long long rows, int cols, const O
   const size_t smem = static_cast<size_t>(W) * static_cast<size_t>(cols) * 4;
   static bool configured = false;  // per instantiation; the attribute is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(octav_rows_warp<NV, FULL>,
+    cudaError_t e = cudaFuncSetAttribute(octav_rows_warp<NV, FULL, SKIP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, W * NV * 512);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octav_rows_warp<NV, FULL>,
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octav_rows_warp<NV, FULL, SKIP>,
                                                                 W * 32, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sm_count) * per_sm;
   const long long need = (rows + W - 1) / W;
   if (grid > need) grid = need;
-  octav_rows_warp<NV, FULL><<<static_cast<unsigned>(grid), W * 32, smem, st>>>(
+  octav_rows_warp<NV, FULL, SKIP><<<static_cast<unsigned>(grid), W * 32, smem, st>>>(
       x, rows, cols, k, iters, trace, notclose);
   return cudaSuccess;
 }
@@ -629,8 +646,12 @@ template <int NV>
 cudaError_t launch_rows_warp(const float* x, long long rows, int cols, const OctavConst& k,
                              int iters, float* trace, unsigned* notclose, int sm_count,
                              cudaStream_t st) {
-  if (cols == NV * 128) return launch_rows_warp_k<NV, true>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
-  return launch_rows_warp_k<NV, false>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
+  static const bool skip = getenv("AEQB_OCTAV_NO_SKIP") == nullptr;  // A/B runs
+  if (cols == NV * 128)
+    return skip ? launch_rows_warp_k<NV, true, true>(x, rows, cols, k, iters, trace, notclose, sm_count, st)
+                : launch_rows_warp_k<NV, true, false>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
+  return skip ? launch_rows_warp_k<NV, false, true>(x, rows, cols, k, iters, trace, notclose, sm_count, st)
+              : launch_rows_warp_k<NV, false, false>(x, rows, cols, k, iters, trace, notclose, sm_count, st);
 }
 
 }  // namespace
