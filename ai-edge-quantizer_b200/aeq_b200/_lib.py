@@ -30,6 +30,10 @@ SIGNATURES = {
     "aeqb_launch_count": (_L, []),
     "aeqb_host_requant_rows_batch_f32": (_I, [_P, _L, _I, _I]),
     "aeqb_host_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I]),
+    "aeqb_host_set_devices": (_I, [_P, _I]),
+    "aeqb_host_worker_threads": (_I, []),
+    "aeqb_host_copy_in": (_I, [_P, _P, _c.c_size_t, _P]),
+    "aeqb_host_copy_out": (_I, [_P, _P, _c.c_size_t, _P]),
     "aeqb_host_alloc": (_P, [_c.c_size_t]),
     "aeqb_host_free": (None, [_P]),
     "aeqb_host_release": (None, []),
@@ -67,6 +71,7 @@ SIGNATURES = {
     "aeqb_quantize_f32": (_I, [_P, _L, _L, _L, _P, _P, _I, _I, _I, _P, _P]),
     "aeqb_dequantize_f32": (_I, [_P, _I, _L, _L, _L, _P, _P, _I, _I, _P, _P]),
     "aeqb_pack_bits": (_I, [_P, _L, _I, _P, _P]),
+    "aeqb_swap_axes": (_I, [_P, _L, _L, _L, _I, _P, _P]),
     "aeqb_requant_mse_rows_f32": (_I, [_P, _L, _L, _I, _F, _P, _P, _P, _P, _P]),
     "aeqb_dwr_workspace_bytes": (_c.c_size_t, [_L, _L]),
     "aeqb_dwr_scales_f32": (_I, [_P, _L, _L, _P, _P, _P]),

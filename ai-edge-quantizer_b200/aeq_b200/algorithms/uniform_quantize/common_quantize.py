@@ -41,13 +41,10 @@ def init_tensor_min_max(tensor_data: Optional[np.ndarray], op_info: qtyping.OpIn
     out_shape = (*shape[:-1], shape[-1] // block)  # keepdims=False
   elif gran == _Gran.CHANNELWISE and (
       qdim := common_utils.get_weight_quantized_dim(op_info, tensor_data, gran)) is not None:
-    if qdim != 0:
-      raise NotImplementedError(
-          f"per-channel min/max along dimension {qdim} is not on the accelerated path yet")
-    x = hostio.to_device(tensor_data.reshape(shape[0], -1), np.float32)
+    x = device.channel_rows(hostio.to_device(tensor_data, np.float32), shape, qdim)
     mn, mx, _ = device.row_stats(x)
     out_shape = [1] * tensor_data.ndim
-    out_shape[0] = shape[0]
+    out_shape[qdim] = shape[qdim]
   elif gran in (_Gran.TENSORWISE, _Gran.CHANNELWISE):
     mm = device.minmax_tensor(hostio.to_device(tensor_data.reshape(-1), np.float32))
     mn, mx = mm[0:1], mm[1:2]

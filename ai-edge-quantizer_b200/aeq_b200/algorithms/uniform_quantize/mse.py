@@ -51,15 +51,13 @@ def get_tensor_quant_params(
   if qdim is None:
     x = hostio.to_device(tensor_content.reshape(1, -1), np.float32)
     pshape = [1] * tensor_content.ndim
-  elif qdim == 0:
-    x = hostio.to_device(tensor_content.reshape(shape[0], -1), np.float32)
-    pshape = [shape[0]] + [1] * (tensor_content.ndim - 1)
-  else:
-    raise NotImplementedError(
-        f"MSE along quantised dimension {qdim} is not on the accelerated path yet")
-  if qdim == 0:  # per channel: scale and integers in one pass over the weight
+  else:  # channels of any axis as rows (dim 0: a view; others: aeqb_swap_axes)
+    x = device.channel_rows(hostio.to_device(tensor_content, np.float32), shape, qdim)
+    pshape = [1] * tensor_content.ndim
+    pshape[qdim] = shape[qdim]
+  if qdim is not None:  # per channel: scale and integers in one pass over the weight
     out = device.requant_mse_rows(x, cfg.num_bits, multiplier)
-    scale, q = out.scale, out.q
+    scale, q = out.scale, device.channel_rows_back(out.q, shape, qdim)
   else:          # whole tensor: grid-wide sum of squares first
     scale = device.mse_scale_rows(x, multiplier)
     q = device.quantize(x, scale.reshape(-1), None, cfg.num_bits, True, x.shape[0], x.shape[1])

@@ -4,6 +4,8 @@ Mirror of ai_edge_quantizer/algorithms/uniform_quantize/naive_min_max_quantize.p
 (`get_tensor_quant_params` :34-110, `min_max_calibrate` :181-226) with the
 arithmetic in the fused sm_100a kernels:
   CHANNELWISE (quantised dim 0) -> aeqb_requant_rows_f32        (one HBM pass)
+  CHANNELWISE (other dims: DEPTHWISE_CONV_2D dim 3, BATCH_MATMUL) -> aeqb_swap_axes moves the
+                                   channel axis to the front, same kernel, integers moved back
   BLOCKWISE_*                   -> aeqb_requant_blocks_f32      (one HBM pass)
   TENSORWISE / QSV min-max      -> aeqb_minmax_tensor_f32 + aeqb_requant_given_minmax_f32
 """
@@ -17,22 +19,13 @@ import numpy as np
 from ... import host
 from ... import hostio
 from ... import qtyping
+from ...transformations import quantize_tensor
 from ..utils import common_utils
 from . import common_quantize
 from . import uniform_quantize_tensor as uqt
 
 ALGORITHM_KEY = "min_max_uniform_quantize"
 _Gran = qtyping.QuantGranularity
-
-
-def _as_rows(tensor_content: np.ndarray, quantized_dim):
-  """2-D [channels, rest] view for a dim-0 per-channel weight (rows are contiguous)."""
-  if quantized_dim != 0:
-    raise NotImplementedError(
-        f"per-channel quantisation along dimension {quantized_dim} is not on the"
-        " accelerated path yet (dimension 0: FULLY_CONNECTED, CONV_2D,"
-        " EMBEDDING_LOOKUP, CONV_2D_TRANSPOSE)")
-  return tensor_content.reshape(tensor_content.shape[0], -1)
 
 
 def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConfig,
@@ -58,7 +51,9 @@ def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConf
     uqt._blockwise_shape(shape, qdim, block)  # reference's divisibility error
     w2 = tensor_content.reshape(-1, shape[-1])
     if clip is None:  # host-buffer pipeline: chunked H2D -> fused kernel -> D2H
-      q, _, scale, _ = host.requant_blocks([w2], block, bits)[0]
+      q, packed, scale, _ = host.requant_blocks([w2], block, bits, want_packed=(bits == 4))[0]
+      if packed is not None:  # QUANTIZE_TENSOR's pack step finds the bytes instead of redoing them
+        quantize_tensor.remember_packed(q, bits, packed)
       scale = scale.reshape(*shape[:-1], shape[-1] // block)
       return qtyping.UniformQuantParams(
           num_bits=bits, quantized_dimension=qdim, scale=scale,
@@ -69,19 +64,25 @@ def quantize_weight(op_info: qtyping.OpInfo, cfg: qtyping.TensorQuantizationConf
     scale = hostio.to_host(out.scale).reshape(*shape[:-1], shape[-1] // block)
     zp = np.zeros(scale.shape, dtype=uqt.numpy_dtype_for(bits))
   elif gran == _Gran.CHANNELWISE and qdim is not None:
-    w2 = _as_rows(tensor_content, qdim)
     pshape = [1] * tensor_content.ndim
     pshape[qdim] = shape[qdim]
-    if clip is None:
-      q, _, scale, zp = host.requant_rows([w2], bits, sym)[0]
+    if clip is None and qdim == 0:
+      w2 = tensor_content.reshape(shape[0], -1)
+      fuse_pack = bits in (2, 4) and w2.shape[1] % (8 // bits) == 0
+      q, packed, scale, zp = host.requant_rows([w2], bits, sym, want_packed=fuse_pack)[0]
+      if packed is not None:
+        quantize_tensor.remember_packed(q, bits, packed)
       return qtyping.UniformQuantParams(
           num_bits=bits, quantized_dimension=qdim, scale=scale.reshape(pshape),
           zero_point=zp.reshape(pshape).astype(uqt.numpy_dtype_for(bits)), symmetric=sym,
           quantized_data=q.reshape(shape), block_size=0)
-    xd = hostio.to_device(w2, np.float32) if x_dev is None else x_dev.reshape(w2.shape)
-    out = device.requant_rows(xd, bits, sym, clip=clip)
+    xd = hostio.to_device(tensor_content, np.float32) if x_dev is None else x_dev
+    out = device.requant_rows(device.channel_rows(xd, shape, qdim), bits, sym, clip=clip)
     scale = hostio.to_host(out.scale).reshape(pshape)
     zp = hostio.to_host(out.zero_point).reshape(pshape).astype(uqt.numpy_dtype_for(bits))
+    return qtyping.UniformQuantParams(
+        num_bits=bits, quantized_dimension=qdim, scale=scale, zero_point=zp, symmetric=sym,
+        quantized_data=hostio.to_host(device.channel_rows_back(out.q, shape, qdim)), block_size=0)
   elif gran in (_Gran.TENSORWISE, _Gran.CHANNELWISE):
     # CHANNELWISE on an op without a quantised-dim entry reduces over everything,
     # like get_reduce_dims(None) -> axis=None in the reference.

@@ -40,10 +40,8 @@ def clipping_constants_device(x_dev, op_info: qtyping.OpInfo,
   qdim = common_utils.get_weight_quantized_dim(op_info, probe, gran)
   if qdim is None:
     return device.octav_clip_rows(x_dev.reshape(1, -1), cfg.num_bits, MAX_ITERATIONS, divisor)
-  if qdim != 0:
-    raise NotImplementedError(
-        f"OCTAV along quantised dimension {qdim} is not on the accelerated path yet")
-  return device.octav_clip_rows(x_dev.reshape(shape[0], -1), cfg.num_bits, MAX_ITERATIONS, divisor)
+  return device.octav_clip_rows(device.channel_rows(x_dev.reshape(tuple(shape)), shape, qdim),
+                                cfg.num_bits, MAX_ITERATIONS, divisor)
 
 
 def guess_clipping_with_octav(x: np.ndarray, bits: int, axis, max_iterations: int = 10,

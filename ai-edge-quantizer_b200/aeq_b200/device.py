@@ -242,6 +242,37 @@ def pack_bits(q: torch.Tensor, bits: int) -> torch.Tensor:
   return out
 
 
+def swap_axes(x: torch.Tensor, a: int, b: int, inner: int) -> torch.Tensor:
+  """x viewed as [a, b, inner] -> contiguous [b, a, inner] (aeqb_swap_axes); fp32 or int8."""
+  if not x.is_cuda or x.element_size() not in (1, 4) or not x.is_contiguous():
+    raise ValueError("expected a contiguous CUDA tensor of 1- or 4-byte elements")
+  if x.numel() != a * b * inner:
+    raise ValueError(f"{x.numel()} elements do not form [{a}, {b}, {inner}]")
+  out = torch.empty((b, a, inner), dtype=x.dtype, device=x.device)
+  _lib.call("aeqb_swap_axes", _ptr(x), a, b, inner, x.element_size(), _ptr(out), _stream())
+  return out
+
+
+def channel_rows(x: torch.Tensor, shape, qdim: int) -> torch.Tensor:
+  """[shape[qdim], rest] matrix whose rows are the channels of axis `qdim` (a view for qdim 0)."""
+  import math
+  c = int(shape[qdim])
+  if qdim == 0:
+    return x.reshape(c, -1)
+  outer, inner = math.prod(shape[:qdim]), math.prod(shape[qdim + 1:])
+  return swap_axes(x.reshape(-1), outer, c, inner).reshape(c, -1)
+
+
+def channel_rows_back(y: torch.Tensor, shape, qdim: int) -> torch.Tensor:
+  """Inverse of `channel_rows`: a [channels, rest] result back in the tensor's own layout."""
+  import math
+  if qdim == 0:
+    return y.reshape(tuple(shape))
+  c = int(shape[qdim])
+  outer, inner = math.prod(shape[:qdim]), math.prod(shape[qdim + 1:])
+  return swap_axes(y.reshape(-1), c, outer, inner).reshape(tuple(shape))
+
+
 # ------------------------------------------------------------------ batched (whole model)
 def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = True,
                        want_packed: bool = False, outs=None, mirror=None):

@@ -44,6 +44,19 @@ def pinned_empty(shape, dtype) -> np.ndarray:
   return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
+def set_devices(devices=None) -> list[int]:
+  """GPUs the host-buffer calls fan out over: a list of device indices, "all" (every visible
+  GPU) or None (default: the current device only).  Returns the list in effect."""
+  _require_gpu()
+  import torch
+  if devices == "all":
+    devices = list(range(torch.cuda.device_count()))
+  devices = [int(d) for d in (devices or [])]
+  arr = (ctypes.c_int * max(1, len(devices)))(*devices)
+  _lib.call("aeqb_host_set_devices", ctypes.cast(arr, ctypes.c_void_p), len(devices))
+  return devices or [torch.cuda.current_device()]
+
+
 def _f32_2d(w: np.ndarray) -> np.ndarray:
   if w.dtype != np.float32:
     raise ValueError(f"only float32 tensors are quantised, got {w.dtype}")

@@ -6,8 +6,13 @@ reference's own materialiser (all its graph bookkeeping, constraints, bias and
 cache logic stay untouched) partially applied to OUR
 `get_tensor_quant_params` — the exact seam the reference uses itself
 (algorithm_manager.py:160-163, 316-319, 415-418, 446-449; signature
-qtyping.py:702-710).  Afterwards `Quantizer.quantize()` / `.calibrate()` reach
-the sm_100a kernels for every weight the accelerated path covers.
+qtyping.py:702-710).  The same registrations also swap the CALIBRATION functions
+(`CalibrationFunc`, algorithm_manager_api.py:97-122: `min_max_calibrate`, `gptq.calibrate`,
+`oscar.calibrate`) for the device ones, and `install` rebinds the pack step of QUANTIZE_TENSOR /
+ADD_DEQUANTIZE (`transformation_utils.pack_data`, looked up at call time by
+transformations/quantize_tensor.py:195-200, which `TransformationPerformer` registers at
+transformation_performer.py:67-93).  Afterwards `Quantizer.quantize()` / `.calibrate()` reach the
+sm_100a kernels for the weights, the activation statistics and the bit packing.
 
     import ai_edge_quantizer.algorithm_manager as am
     import aeq_b200.plugin
@@ -104,11 +109,58 @@ def uninstall() -> None:
     fn(*args)
 
 
-def install(reference_algorithm_manager, algorithms=None) -> list[str]:
-  """Re-registers the reference's ops with device-backed arithmetic; returns the keys bound."""
+def _device_calibration_func(am, ref_func):
+  """Our device calibration function for one of the reference's, or None when it has no twin."""
+  from .algorithms.uniform_quantize import naive_min_max_quantize as ours_nmm
+  twins = []
+  for mod_name, attr, ours in (("naive_min_max_quantize", "min_max_calibrate", ours_nmm.min_max_calibrate),
+                               ("gptq", "calibrate", gptq.calibrate),
+                               ("oscar", "calibrate", oscar.calibrate),
+                               ("dequantized_weight_recovery", "calibrate",
+                                dequantized_weight_recovery.calibrate)):
+    mod = getattr(am, mod_name, None)
+    if mod is not None and getattr(mod, attr, None) is not None:
+      twins.append((getattr(mod, attr), ours))
+  for theirs, ours in twins:
+    if ref_func is theirs:
+      return ours
+  return None
+
+
+def install_pack(reference_transformation_utils) -> None:
+  """Rebinds `transformation_utils.pack_data` (transformations/transformation_utils.py:293-353)
+  to the device pack: INT4 / INT2 bytes come from `aeqb_pack_bits`, or straight from the fused
+  requantisation pass when the integers were produced by this package."""
+  tu = reference_transformation_utils
+  if getattr(tu.pack_data, "_aeqb200", False):
+    return
+  from .transformations import quantize_tensor as ours_qt
+
+  def pack_data(bitwidth: int, data):
+    return ours_qt.pack_data(bitwidth, data)
+
+  pack_data._aeqb200 = True
+  _saved.append((setattr, (tu, "pack_data", tu.pack_data)))
+  tu.pack_data = pack_data
+
+
+def install(reference_algorithm_manager, algorithms=None, calibration: bool = True,
+            pack: bool = True) -> list[str]:
+  """Re-registers the reference's ops with device-backed arithmetic; returns the keys bound.
+
+  calibration: also swap each op's calibration function for its device twin (the reference's
+               `Calibrator` then reduces activations on the GPU, calibrator.py:545-582).
+  pack:        also rebind `transformation_utils.pack_data` of the reference package.
+  """
   am = reference_algorithm_manager
   ref_qtyping = am.qtyping
   bound = []
+
+  def calib_for(key, op_name):
+    theirs = am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE)
+    ours = _device_calibration_func(am, theirs) if calibration else None
+    return theirs if ours is None else ours
+
   for key, (dict_attr, fn, ref_module) in _BINDINGS.items():
     if algorithms is not None and key not in algorithms:
       continue
@@ -126,7 +178,7 @@ def install(reference_algorithm_manager, algorithms=None) -> list[str]:
           am.get_update_qsv_func(key, op_name))))
       am.register_quantized_op(
           key, op_name, mod.init_qsvs,
-          calibration_func=am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE),
+          calibration_func=calib_for(key, op_name),
           materialize_func=functools.partial(inner, adapted),
           update_qsv_func=am.get_update_qsv_func(key, op_name))
     bound.append(key)
@@ -141,7 +193,23 @@ def install(reference_algorithm_manager, algorithms=None) -> list[str]:
       adapted._aeqb200 = True
       _saved.append((setattr, (mod, "get_tensor_quant_params", mod.get_tensor_quant_params)))
       mod.get_tensor_quant_params = adapted
+    if calibration and am.is_algorithm_registered(key):
+      for op_name in am.get_supported_ops(key):
+        theirs = am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.CALIBRATE)
+        ours = _device_calibration_func(am, theirs)
+        if ours is None:
+          continue
+        args = (key, op_name, am.get_init_qsv_func(key, op_name), theirs,
+                am.get_quantization_func(key, op_name, ref_qtyping.QuantizeMode.MATERIALIZE),
+                am.get_update_qsv_func(key, op_name))
+        _saved.append((am.register_quantized_op, args))
+        am.register_quantized_op(args[0], args[1], args[2], calibration_func=ours,
+                                 materialize_func=args[4], update_qsv_func=args[5])
     bound.append(key)
+  if pack:
+    import importlib
+    pkg = am.__name__.rsplit(".", 1)[0]
+    install_pack(importlib.import_module(pkg + ".transformations.transformation_utils"))
   return bound
 
 

@@ -19,6 +19,7 @@ import numpy as np
 from . import host
 from . import qtyping
 from .algorithms.uniform_quantize import uniform_quantize_tensor as uqt
+from .transformations import quantize_tensor
 from .utils import tfl_flatbuffer_utils
 
 # op name -> quantised dimension of its weight when CHANNELWISE (dim 0 is the only layout the
@@ -88,8 +89,11 @@ def prefetch_weights(items: Iterable, cache, make_params: Optional[Callable] = N
     if gkey[0] == "rows":
       _, sym, bits = gkey
       ws = [d.reshape(d.shape[0], -1) for _, _, d in members]
-      outs = host.requant_rows(ws, bits, sym)
-      for (buf, cfg, d), (q, _, scale, zp) in zip(members, outs):
+      fuse_pack = bits in (2, 4) and all(w.shape[1] % (8 // bits) == 0 for w in ws)
+      outs = host.requant_rows(ws, bits, sym, want_packed=fuse_pack)
+      for (buf, cfg, d), (q, packed, scale, zp) in zip(members, outs):
+        if packed is not None:
+          quantize_tensor.remember_packed(q, bits, packed)
         pshape = [d.shape[0]] + [1] * (d.ndim - 1)
         cache.insert(buf, cfg, make_params(
             num_bits=bits, quantized_dimension=0, scale=scale.reshape(pshape),
@@ -98,8 +102,10 @@ def prefetch_weights(items: Iterable, cache, make_params: Optional[Callable] = N
     else:
       _, block, bits = gkey
       ws = [d.reshape(-1, d.shape[-1]) for _, _, d in members]
-      outs = host.requant_blocks(ws, block, bits)
-      for (buf, cfg, d), (q, _, scale, _) in zip(members, outs):
+      outs = host.requant_blocks(ws, block, bits, want_packed=(bits == 4))
+      for (buf, cfg, d), (q, packed, scale, _) in zip(members, outs):
+        if packed is not None:
+          quantize_tensor.remember_packed(q, bits, packed)
         sshape = (*d.shape[:-1], d.shape[-1] // block)
         cache.insert(buf, cfg, make_params(
             num_bits=bits, quantized_dimension=d.ndim - 1, scale=scale.reshape(sshape),

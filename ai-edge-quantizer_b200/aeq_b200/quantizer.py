@@ -24,6 +24,7 @@ import pathlib
 from typing import Optional, Union
 
 from . import algorithm_manager
+from . import prefetch
 from . import qtyping
 from . import recipe_manager
 from .algorithms.utils import common_utils
@@ -73,6 +74,7 @@ class Quantizer:
     if quantization_recipe is not None:
       self.load_quantization_recipe(quantization_recipe)
     self._result = QuantizationResult([{}], None)
+    self.prefetch_stats: dict = {}
 
   # ---- recipe
   def load_quantization_recipe(self, recipe) -> None:
@@ -114,6 +116,23 @@ class Quantizer:
     cache = common_utils.TensorQuantParamsCache()
     qsvs = calibration_result or {}
     out = []
+    # Batched driver first: every min-max weight of the model goes through
+    # ONE pipelined host-buffer call per (granularity, bits) group and lands in the cache, so
+    # the per-op walk below (params_generator.py:110-183) finds its constants already done.
+    items = []
+    for subgraph in model.subgraphs:
+      graph_info = qtyping.GraphInfo(subgraph.tensors, model.buffers)
+      for op_index, op in enumerate(subgraph.operators):
+        code = tfl_model.builtin_code(model.operatorCodes[op.opcodeIndex])
+        if code not in fu.TFL_OP_CODE_TO_NAME:
+          continue
+        op_name = fu.TFL_OP_CODE_TO_NAME[code]
+        alg, cfg = self._recipe_manager.get_quantization_configs(
+            op_name, fu.get_op_scope(op, subgraph.tensors))
+        if alg == AlgorithmName.MIN_MAX_UNIFORM_QUANT.value and cfg.weight_tensor_config is not None:
+          items.append((qtyping.OpInfo(op, op_name, op_index, cfg), graph_info))
+    if items:
+      self.prefetch_stats = prefetch.prefetch_weights(items, cache)
     for sg_index, subgraph in enumerate(model.subgraphs):
       graph_info = qtyping.GraphInfo(subgraph.tensors, model.buffers)
       for op_index, op in enumerate(subgraph.operators):
@@ -163,11 +182,13 @@ class Quantizer:
       for tid, (prm, consumers) in by_tensor.items():
         qt.insert_dequant(model, subgraph, tid, prm, consumers, buffer_origin)
 
-  def quantize(self, calibration_result=None, serialize_to_path=None) -> QuantizationResult:
+  def quantize(self, calibration_result=None, serialize_to_path=None,
+               external_buffers: Optional[bool] = None) -> QuantizationResult:
+    """`external_buffers`: None = automatic (payloads of 2 GB and more leave the flatbuffer)."""
     if not self.get_quantization_recipe():
       raise RuntimeError("Can not quantize without a quantization recipe.")
     self._apply(self._generate_params(calibration_result))
-    data = fu.write_model_to_bytes(self._float_model)
+    data = tfl_model.write_model_to_bytes(self._float_model, external_buffers)
     if serialize_to_path is not None:
       with open(serialize_to_path, "wb") as f:
         f.write(data)

@@ -56,32 +56,59 @@ def _world(group) -> tuple[int, int]:
   return 0, 1
 
 
+def _vote(err, group, device) -> None:
+  """All ranks raise together or none does: a one-sided raise before a collective would leave
+  the other ranks waiting in it (same rule as peer.PeerScales._vote)."""
+  rank, world = _world(group)
+  if world > 1:
+    ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0 and err is None:
+      err = RuntimeError("allgather_vectors: another rank reported an error; no data was exchanged")
+  if err is not None:
+    raise err
+
+
 def allgather_vectors(local: dict[int, torch.Tensor], lengths: Sequence[int], owner: Sequence[int],
-                      group=None) -> list[torch.Tensor]:
+                      group=None, dtype: Optional[torch.dtype] = None,
+                      device: Optional[torch.device] = None) -> list[torch.Tensor]:
   """All ranks end up with every tensor's vector.
 
   local:   {tensor index: 1-D tensor} for the tensors this rank owns (all one dtype / device).
   lengths: vector length of EVERY tensor (known everywhere: it follows from the shapes).
+  dtype / device: needed only by a rank that owns no tensor (fewer tensors than ranks): it then
+           contributes a zero-filled row instead of guessing.
   One all_gather_into_tensor of a [world, max_rank_len] buffer; rank r's slots are its
-  tensors in index order, so offsets need no exchange.
+  tensors in index order, so offsets need no exchange.  Argument errors are voted on first, so
+  that every rank raises or none does.
   """
   rank, world = _world(group)
   mine = owned(owner, rank)
-  if sorted(local) != mine:
-    raise ValueError(f"rank {rank} must supply exactly the tensors it owns: {mine}")
   per_rank = [sum(int(lengths[i]) for i in owned(owner, r)) for r in range(world)]
   width = max(per_rank) if per_rank else 0
-  if not local and width == 0:
-    return [torch.empty(0) for _ in lengths]
   proto = next(iter(local.values())) if local else None
-  if world > 1 and proto is None:
-    raise ValueError("a rank without tensors cannot infer dtype / device; give every rank work")
-  flat = torch.zeros(width, dtype=proto.dtype, device=proto.device)
+  dtype = proto.dtype if proto is not None else dtype
+  device = proto.device if proto is not None else device
+  err = None
+  if sorted(local) != mine:
+    err = ValueError(f"rank {rank} must supply exactly the tensors it owns: {mine}")
+  elif world > 1 and width > 0 and (dtype is None or device is None):
+    err = ValueError("a rank without tensors must be given dtype= and device= to join the all-gather")
+  else:
+    for i in mine:
+      if local[i].numel() != int(lengths[i]):
+        err = ValueError(f"tensor {i}: expected {lengths[i]} values, got {local[i].numel()}")
+        break
+  if device is None:  # nothing to infer from: the vote itself runs on the backend's default
+    device = torch.device("cuda", torch.cuda.current_device()) if (
+        world > 1 and dist.get_backend(group) == "nccl") else torch.device("cpu")
+  _vote(err, group, device)
+  if width == 0:
+    return [torch.empty(0, dtype=dtype or torch.float32) for _ in lengths]
+  flat = torch.zeros(width, dtype=dtype, device=device)
   off = 0
   for i in mine:
     v = local[i].reshape(-1)
-    if v.numel() != int(lengths[i]):
-      raise ValueError(f"tensor {i}: expected {lengths[i]} values, got {v.numel()}")
     flat[off:off + v.numel()] = v
     off += v.numel()
   if world == 1:
@@ -120,5 +147,6 @@ def requantize_sharded(weights: Sequence[np.ndarray], compute: Callable[[list[np
   for i, res in zip(mine, results):
     s = torch.from_numpy(np.ascontiguousarray(res[2]).reshape(-1))
     local[i] = s.to(device) if device is not None else s
-  scales = allgather_vectors(local, [scale_length(w) for w in weights], owner, group)
+  scales = allgather_vectors(local, [scale_length(w) for w in weights], owner, group,
+                             dtype=torch.float32, device=device or torch.device("cpu"))
   return owner, dict(zip(mine, results)), scales

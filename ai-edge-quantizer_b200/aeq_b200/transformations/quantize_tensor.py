@@ -8,6 +8,8 @@ Bit packing of INT4 / INT2 payloads runs on the device (`aeqb_pack_bits`).
 """
 from __future__ import annotations
 
+import weakref
+
 import ml_dtypes
 import numpy as np
 
@@ -16,30 +18,69 @@ from .. import qtyping
 from ..utils import tfl_model as tm
 
 
+# The fused requantisation kernels write the packed INT4 / INT2 bytes in the same pass that
+# produces the one-value-per-byte `quantized_data` the reference's dataclass carries; the packed
+# copy is remembered here, keyed by the identity of the integer array, so that QUANTIZE_TENSOR's
+# pack step (quantize_tensor.py:195-200) finds it instead of shipping the integers to the device
+# again.  Entries die with their array.
+_packed_by_array: dict = {}
+
+
+def _owner(a: np.ndarray) -> np.ndarray:
+  """The ndarray at the end of the `.base` chain (views collapse onto it)."""
+  while isinstance(a.base, np.ndarray):
+    a = a.base
+  return a
+
+
+def remember_packed(quantized_data: np.ndarray, bitwidth: int, packed: np.ndarray) -> None:
+  own = _owner(quantized_data)
+  if own.size != quantized_data.size:
+    return  # a slice of something larger: identity would not identify it
+  key = id(own)
+  _packed_by_array[key] = (weakref.ref(own, lambda _r, k=key: _packed_by_array.pop(k, None)),
+                           bitwidth, packed)
+
+
+def lookup_packed(data: np.ndarray, bitwidth: int):
+  """Packed bytes remembered for the array `data` is a whole (flat, reinterpreted) view of."""
+  own = _owner(data)
+  hit = _packed_by_array.get(id(own))
+  if hit is not None and hit[0]() is own and hit[1] == bitwidth and own.size == data.size:
+    return hit[2]
+  return None
+
+
 def pack_data(bitwidth: int, flattened_data: np.ndarray) -> np.ndarray:
   """INT4: two values per byte (even index low); INT2: four per byte; other widths pass."""
+  flattened_data = flattened_data.reshape(-1)
   if bitwidth not in (2, 4):
     return flattened_data
+  hit = lookup_packed(flattened_data, bitwidth)
+  if hit is not None:
+    return hit
   from .. import device
   q = hostio.to_device(np.ascontiguousarray(flattened_data).view(np.int8), np.int8)
   return hostio.to_host(device.pack_bits(q, bitwidth))
 
 
 def quant_params_to_tflite_type(bitwidth: int) -> int:
-  """Narrowest TFLite integer type (reference :31-57)."""
+  """TFLite integer type of a bit width, the reference's table (quantize_tensor.py:29-55):
+  exactly 2 -> INT2, exactly 4 -> INT4 (the two packed widths), any other width up to 8 ->
+  INT8 (3-, 5-, 6-, 7-bit values travel one per byte), then INT16 / INT32 / INT64."""
   if bitwidth == 2:
     return tm.TensorType.INT2
-  if bitwidth <= 4:
+  if bitwidth == 4:
     return tm.TensorType.INT4
-  if bitwidth <= 8:
+  if 1 < bitwidth <= 8:
     return tm.TensorType.INT8
-  if bitwidth <= 16:
+  if 8 < bitwidth <= 16:
     return tm.TensorType.INT16
-  if bitwidth <= 32:
+  if 16 < bitwidth <= 32:
     return tm.TensorType.INT32
-  if bitwidth <= 64:
+  if 32 < bitwidth <= 64:
     return tm.TensorType.INT64
-  raise ValueError(f"Unsupported quant params: {bitwidth}")
+  raise ValueError(f"Unsupported bitwidth {bitwidth}.I")
 
 
 def add_new_constant_tensor(name: bytes, data: np.ndarray, tensor_type: int, subgraph, model) -> int:
@@ -84,9 +125,12 @@ def quantize_tensor(model, subgraph, tensor_id: int, params, buffer_origin: dict
                            else _blockwise(params, tensor, subgraph, model))
     tensor.type = quant_params_to_tflite_type(params.num_bits)
   elif isinstance(params, qtyping.NonLinearQuantParams):
-    if params.num_bits != 16:
+    if params.num_bits == 16:
+      tensor.type = tm.TensorType.FLOAT16
+    elif params.num_bits == 32:
+      tensor.type = tm.TensorType.FLOAT32
+    else:
       raise ValueError(f"Unsupported nonlinear params: {params.num_bits}")
-    tensor.type = tm.TensorType.FLOAT16
 
 
 def _opcode_index(model, builtin: int) -> int:

@@ -58,7 +58,8 @@ TFL_OP_TO_BLOCKWISE_WEIGHT_QUANTIZED_DIM = qtyping.FrozenParams({
 
 # TensorType codes of the TFLite schema that this path can meet.
 TENSOR_TYPE_TO_NUMPY = {0: np.float32, 1: np.float16, 2: np.int32, 3: np.uint8,
-                        4: np.int64, 7: np.int16, 9: np.int8}
+                        4: np.int64, 6: np.bool_, 7: np.int16, 9: np.int8, 10: np.float64,
+                        12: np.uint64, 15: np.uint32, 16: np.uint16}
 
 
 def get_tensor_name(tensor) -> str:
@@ -74,6 +75,7 @@ def get_tensor_data(tensor, buffers):
   if raw is None or len(raw) == 0:
     return None
   dtype = TENSOR_TYPE_TO_NUMPY.get(getattr(tensor, "type", 0))
-  if dtype is None:
-    raise ValueError(f"unsupported tensor type code {tensor.type}")
-  return np.frombuffer(raw, dtype=dtype).reshape(tuple(tensor.shape))
+  if dtype is None:  # packed INT4 / strings / resources: a constant, but not one this path reads
+    return np.frombuffer(raw, dtype=np.uint8)
+  data = np.frombuffer(raw, dtype=dtype)
+  return data if tensor.shape is None else data.reshape(tuple(tensor.shape))

@@ -19,6 +19,7 @@ from __future__ import annotations
 import dataclasses
 import mmap
 import os
+import struct
 from typing import Any, Optional
 
 import numpy as np
@@ -443,24 +444,42 @@ def _write_subgraph(b: fb.Builder, g: SubGraphT) -> int:
   return b.end_table()
 
 
-def write_model_to_bytes(m: ModelT) -> bytes:
+EXTERNAL_BUFFER_THRESHOLD = (1 << 31) - (1 << 24)
+
+
+def _payload(x: BufferT):
+  if x.data is None or len(x.data) == 0:
+    return None
+  if isinstance(x.data, (bytes, bytearray, memoryview)):
+    return x.data
+  return np.ascontiguousarray(np.asarray(x.data).view(np.uint8) if isinstance(x.data, np.ndarray) else x.data)
+
+
+def write_model_to_bytes(m: ModelT, external_buffers: Optional[bool] = None):
   """Serialises the object tree.  Buffer payloads are 16-byte aligned like the schema's
-  `force_align: 16` (and the reference's external-buffer writer, model_modifier.py:36-38)."""
-  total = sum(0 if x.data is None else len(x.data) for x in m.buffers)
-  if total >= (1 << 31) - (1 << 24):
-    raise NotImplementedError("models over 2 GB need external buffers (offset / size), not written here")
-  b = fb.Builder(max(1 << 16, int(total * 1.05) + (1 << 16)))
+  `force_align: 16`.  A flatbuffer addresses 2 GB, so when the payloads reach that size (or
+  `external_buffers=True`) they are written AFTER the flatbuffer, each 16-byte aligned, and the
+  buffer tables carry `offset` / `size` instead of `data` — the layout of the reference's
+  `ModelModifier._serialize_model` (model_modifier.py:290-377), which is also what
+  `read_model_from_bytes` resolves back into views."""
+  payloads = [_payload(x) for x in m.buffers]
+  total = sum(0 if p is None else len(p) for p in payloads)
+  if external_buffers is None:
+    external_buffers = total >= EXTERNAL_BUFFER_THRESHOLD
+  b = fb.Builder(max(1 << 16, (0 if external_buffers else int(total * 1.05)) + (1 << 16)))
   buffers = []
-  for x in m.buffers:
+  for x, payload in zip(m.buffers, payloads):
     data = 0
-    if x.data is not None and len(x.data) > 0:
-      payload = x.data if isinstance(x.data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(
-          np.asarray(x.data).view(np.uint8) if isinstance(x.data, np.ndarray) else x.data)
+    if payload is not None and not external_buffers:
       data = b.create_byte_vector(payload, align=16)
     b.start_table()
     b.add_offset(0, data)
-    b.add_scalar(1, "ulong", int(x.offset))
-    b.add_scalar(2, "ulong", int(x.size))
+    if payload is not None and external_buffers:
+      b.add_scalar(1, "ulong", 1)  # placeholders: non-default, so the fields exist and can be
+      b.add_scalar(2, "ulong", 1)  # patched once the payload positions are known
+    else:
+      b.add_scalar(1, "ulong", int(x.offset))
+      b.add_scalar(2, "ulong", int(x.size))
     buffers.append(b.end_table())
   buffers_v = b.create_offset_vector(buffers)
   codes = []
@@ -513,7 +532,23 @@ def write_model_to_bytes(m: ModelT) -> bytes:
   b.add_offset(5, mbuf)
   b.add_offset(6, meta_v)
   b.add_offset(7, sigs_v)
-  return b.finish(b.end_table(), FILE_IDENTIFIER)
+  head = b.finish(b.end_table(), FILE_IDENTIFIER)
+  if not external_buffers:
+    return head
+  r16 = lambda n: (n + 15) & ~15
+  out = bytearray(r16(len(head)) + sum(r16(len(p)) for p in payloads if p is not None))
+  out[:len(head)] = head
+  tables = fb.Table.root(head).table_vector(4)
+  pos = r16(len(head))
+  for t, payload in zip(tables, payloads):
+    if payload is None:
+      continue
+    n = len(payload)
+    struct.pack_into("<Q", out, t._field(1), pos)  # pylint: disable=protected-access
+    struct.pack_into("<Q", out, t._field(2), n)    # pylint: disable=protected-access
+    out[pos:pos + n] = memoryview(payload).cast("B")
+    pos = r16(pos + n)
+  return out
 
 
 def write_model(m: ModelT, path: str) -> None:

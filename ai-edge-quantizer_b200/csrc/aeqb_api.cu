@@ -511,6 +511,16 @@ int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* str
                "aeqb_pack_bits");
 }
 
+int aeqb_swap_axes(const void* x, int64_t a, int64_t b, int64_t inner, int elem_bytes, void* out,
+                   void* stream) {
+  if (elem_bytes != 1 && elem_bytes != 4) return fail("elem_bytes must be 1 or 4");
+  if (a < 0 || b < 0 || inner < 0) return fail("bad shape [%lld, %lld, %lld]", (long long)a, (long long)b, (long long)inner);
+  if (a * b * inner > 0 && (!x || !out)) return fail("x / out are NULL");
+  if (x == out && a * b * inner > 0) return fail("swap_axes cannot run in place");
+  return check(aeqb::launch_swap_axes(x, a, b, inner, elem_bytes, out, sm_count(),
+                                      static_cast<cudaStream_t>(stream)), "aeqb_swap_axes");
+}
+
 size_t aeqb_dwr_workspace_bytes(int64_t n_groups, int64_t group_len) {
   return (n_groups > 0 && group_len > 0) ? aeqb::dwr_workspace_bytes(n_groups, group_len) : 0;
 }

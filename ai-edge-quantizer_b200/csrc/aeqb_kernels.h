@@ -193,6 +193,8 @@ cudaError_t launch_dwr_scales(const float* x, long long n_groups, long long glen
 cudaError_t launch_max_abs_diff(const float* a, const float* b, long long n, float* out, void* ws,
                                 int sm_count, cudaStream_t st);
 cudaError_t launch_cast_f16(const float* x, long long n, void* out, int sm_count, cudaStream_t st);
+cudaError_t launch_swap_axes(const void* in, long long a, long long b, long long inner,
+                             int elem_bytes, void* out, int sm_count, cudaStream_t st);
 cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, int sm_count,
                         cudaStream_t st);
 

@@ -104,6 +104,42 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- axis swap
+// out[j, i, t] = in[i, j, t] for in viewed as [a, b, inner]: moves the quantised axis of a
+// DEPTHWISE_CONV_2D ([1, H, W, C], dim 3) or BATCH_MATMUL weight to the front so the row
+// kernels apply, and the integers back (tfl_flatbuffer_utils.py:95-106 lists the dims).
+// inner == 1: 32 x 32 shared-memory tile transpose, both sides coalesced; inner > 1: one
+// thread per output element (runs of `inner` elements stay contiguous on both sides).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    transpose_tile_kernel(const T* __restrict__ in, long long a, long long b, T* __restrict__ out) {
+  __shared__ T tile[32][33];
+  const long long tiles_b = (b + 31) / 32;
+  const long long tb = blockIdx.x % tiles_b, ta = blockIdx.x / tiles_b;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const long long i = ta * 32 + r, j = tb * 32 + tx;
+    if (i < a && j < b) tile[r][tx] = in[i * b + j];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const long long j = tb * 32 + r, i = ta * 32 + tx;
+    if (i < a && j < b) out[j * a + i] = tile[tx][r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    swap_axes_kernel(const T* __restrict__ in, long long a, long long b, long long inner,
+                     T* __restrict__ out, long long n) {
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < n; o += step) {
+    const long long t = o % inner, ji = o / inner;
+    const long long i = ji % a, j = ji / a;
+    out[o] = in[(i * b + j) * inner + t];
+  }
+}
+
 unsigned grid_for(long long n, int sm_count) {
   long long g = (n + 255) / 256;
   const long long cap = static_cast<long long>(sm_count) * 16;
@@ -160,6 +196,30 @@ cudaError_t launch_pack(const int8_t* q, long long n, int bits, uint8_t* out, in
   const long long n_out = (n * bits + 7) / 8;
   pack_kernel<<<grid_for(n_out, sm_count), 256, 0, st>>>(q, n, bits, out, n_out);
   return count_launch();
+}
+
+template <typename T>
+static cudaError_t swap_axes_t(const T* in, long long a, long long b, long long inner, T* out,
+                               int sm_count, cudaStream_t st) {
+  if (inner == 1) {
+    const long long tiles = ((a + 31) / 32) * ((b + 31) / 32);
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    transpose_tile_kernel<T><<<static_cast<unsigned>(tiles), 256, 0, st>>>(in, a, b, out);
+  } else {
+    const long long n = a * b * inner;
+    swap_axes_kernel<T><<<grid_for(n, sm_count), 256, 0, st>>>(in, a, b, inner, out, n);
+  }
+  return count_launch();
+}
+
+cudaError_t launch_swap_axes(const void* in, long long a, long long b, long long inner,
+                             int elem_bytes, void* out, int sm_count, cudaStream_t st) {
+  if (a <= 0 || b <= 0 || inner <= 0) return cudaSuccess;
+  if (elem_bytes == 4)
+    return swap_axes_t(static_cast<const uint32_t*>(in), a, b, inner, static_cast<uint32_t*>(out), sm_count, st);
+  if (elem_bytes == 1)
+    return swap_axes_t(static_cast<const uint8_t*>(in), a, b, inner, static_cast<uint8_t*>(out), sm_count, st);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace aeqb

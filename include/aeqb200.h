@@ -136,14 +136,32 @@ AEQB_API int aeqb_peer_free(void* ptr);
  * The call a NumPy caller makes (naive_min_max_quantize.get_tensor_quant_params,
  * :34-110, over every weight of a model): HOST pointers in the job structs, in
  * and out.  Tensors are cut into ~32 MiB row chunks and pipelined
- * copy-in -> H2D -> fused kernel -> D2H -> copy-out over 4 slots / streams;
+ * copy-in -> H2D -> fused kernel -> D2H -> copy-out over 6 slots / streams per device;
  * page-locked ranges (aeqb_host_alloc, cudaHostRegister) are DMA'd in place,
- * pageable ones are staged.  Returns when every output is in host memory.
+ * pageable ones (the reference's mmap views) are staged by a pool of worker threads bound to
+ * the GPU's NUMA node.  Returns when every output is in host memory.  On any error the pipeline
+ * is drained first: nothing keeps a pointer into the caller's arrays.
  * `clip` must be NULL here. */
 AEQB_API int aeqb_host_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
                                               int symmetric);
 AEQB_API int aeqb_host_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs,
                                                 int block, int bits);
+/* Which GPUs of the node the host-buffer calls above fan out over (chunks are dealt round-robin,
+ * every device has its own ring of slots, streams and staging workers).  n == 0 restores the
+ * default: the calling thread's current device only — under one-process-per-GPU launchers every
+ * rank sees every GPU and must stay on its own.  The reference walks one tensor at a time in one
+ * process (params_generator.py:110-183); this is that process driving the whole node. */
+AEQB_API int aeqb_host_set_devices(const int* devices, int n);
+/* Staging worker threads currently alive (0 before the first host-buffer call). */
+AEQB_API int aeqb_host_worker_threads(void);
+/* Pageable host memory -> device and back through the same pinned ring and worker threads
+ * (what `torch.from_numpy(x).to(device)` does with one thread): the upload of a weight for the
+ * per-tensor algorithms (octav / hadamard_rotation / gptq get_tensor_quant_params take the same
+ * read-only mmap views, utils/tfl_flatbuffer_utils.py:254-263) and the download of their
+ * results.  copy_in returns when the bytes are in device memory; copy_out first waits for
+ * `stream` (the producer of src_device) and returns when the bytes are in dst_host. */
+AEQB_API int aeqb_host_copy_in(void* dst_device, const void* src_host, size_t bytes, void* stream);
+AEQB_API int aeqb_host_copy_out(void* dst_host, const void* src_device, size_t bytes, void* stream);
 /* Page-locked host memory for callers that want zero-copy staging. */
 AEQB_API void* aeqb_host_alloc(size_t bytes);
 AEQB_API void aeqb_host_free(void* p);
@@ -292,6 +310,15 @@ AEQB_API int aeqb_dequantize_f32(const void* q, int q_bytes, int64_t n, int64_t 
  * INT4 two nibbles per byte (even index low), INT2 four crumbs per byte (index 0
  * lowest), odd tail zero padded.  out: ceil(n*bits/8) bytes.  bits 2 or 4. */
 AEQB_API int aeqb_pack_bits(const int8_t* q, int64_t n, int bits, uint8_t* out, void* stream);
+
+/* out[j, i, t] = x[i, j, t] for x viewed as [a, b, inner] (elem_bytes 4: fp32, 1: int8).  Moves
+ * the quantised axis of weights whose channels are not dim 0 (DEPTHWISE_CONV_2D dim 3,
+ * BATCH_MATMUL rank-1 / rank-2: utils/tfl_flatbuffer_utils.py:95-106,
+ * algorithms/utils/common_utils.py:1210-1218) to the front, so that the per-channel reduction of
+ * common_quantize.init_tensor_min_max (common_quantize.py:1337-1344, reduce all dims but the
+ * quantised one) is the row kernels' reduction, and moves the integers back.  Not in place. */
+AEQB_API int aeqb_swap_axes(const void* x, int64_t a, int64_t b, int64_t inner, int elem_bytes,
+                            void* out, void* stream);
 
 /* mse.get_tensor_quant_params fused (algorithms/uniform_quantize/mse.py:36-128, per channel):
  * scale[r] = multiplier * sqrt(mean(x[r]^2)) (fp32 squares, fp64 sum, fp32 mean / sqrt /

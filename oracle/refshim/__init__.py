@@ -3,8 +3,12 @@
 TEST INFRASTRUCTURE ONLY. It exists so that (a) tests/golden/ fixtures can be
 generated from the *unmodified* reference and (b) CPU-side tests in the build
 container can cross-check `oracle/` against the reference when
-`/root/reference` is mounted. The GPU box has no /root/reference; nothing on
-the product path, in `-m gpu` tests, `smoke()` or `bench.py` imports this.
+`/root/reference` is mounted. The GPU box has no /root/reference: there the
+shim resolves to `oracle/_ref/` (the reference's own sources copied byte for
+byte by the committed `oracle/make_ref.py`; git-ignored, shipped with the
+snapshot like the built `.so`), so `-m gpu` tests and `bench.py --impl
+reference` can run the UNMODIFIED reference beside the device path. Nothing
+under `aeq_b200/` (the product) imports this.
 
 Recipe: put stub packages for the absent wheels
 (`immutabledict`, `ai_edge_litert.tools.*`) on sys.path and pre-register an
@@ -17,12 +21,30 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("AEQ_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+_TRAVELLING = os.path.normpath(os.path.join(_HERE, "..", "_ref"))
+
+
+def _find_root() -> str:
+  """/root/reference (build container) first, then the travelling copy oracle/_ref."""
+  env = os.environ.get("AEQ_REFERENCE_ROOT")
+  for cand in ([env] if env else []) + ["/root/reference", _TRAVELLING]:
+    if os.path.isdir(os.path.join(cand, "ai_edge_quantizer")):
+      return cand
+  return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
   return os.path.isdir(os.path.join(REFERENCE_ROOT, "ai_edge_quantizer"))
+
+
+def kind() -> str:
+  """"reference" (the mounted tree) or "_ref" (oracle/_ref, the travelling byte-for-byte copy)."""
+  return "_ref" if os.path.normpath(REFERENCE_ROOT) == _TRAVELLING else "reference"
 
 
 def install() -> None:

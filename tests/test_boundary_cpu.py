@@ -257,6 +257,8 @@ def test_plugin_installs_into_reference_registry():
   ram = refshim.ref("algorithm_manager")
   rq = ram.qtyping
   ref_had = ram.hadamard_rotation.get_tensor_quant_params
+  ref_tu = refshim.ref("transformations.transformation_utils")
+  ref_pack = ref_tu.pack_data
   bound = plugin.install(ram)
   try:
     assert {"min_max_uniform_quantize", "OCTAV", "MSE", "HADAMARD_ROTATION", "GPTQ", "OSCAR",
@@ -270,12 +272,36 @@ def test_plugin_installs_into_reference_registry():
                                   rq.QuantizeMode.MATERIALIZE)
     assert f.func.__name__ == "materialize_transpose"
     assert ram.hadamard_rotation.get_tensor_quant_params is not ref_had
+    # calibration functions (algorithm_manager_api.py:97-122) are the device twins ...
+    FC, CAL = rq.TFLOperationName.FULLY_CONNECTED, rq.QuantizeMode.CALIBRATE
+    for key, name in (("min_max_uniform_quantize", "min_max_calibrate"), ("OCTAV", "min_max_calibrate"),
+                      ("HADAMARD_ROTATION", "min_max_calibrate"), ("GPTQ", "calibrate"),
+                      ("OSCAR", "calibrate")):
+      c = ram.get_quantization_func(key, FC, CAL)
+      assert c.__module__.startswith("aeq_b200.") and c.__name__ == name, (key, c)
+    assert ram.get_quantization_func("min_max_uniform_quantize", rq.TFLOperationName.TRANSPOSE, CAL
+                                     ).__module__.startswith("aeq_b200.")
+    # ... the QSV merges stay the reference's, and the pack step of QUANTIZE_TENSOR is rebound
+    assert ram.get_update_qsv_func("GPTQ", FC).__module__.startswith("ai_edge_quantizer.")
+    assert getattr(ref_tu.pack_data, "_aeqb200", False)
+    assert np.array_equal(ref_tu.pack_data(8, np.arange(6, dtype=np.uint8)), np.arange(6, dtype=np.uint8))
   finally:
     plugin.uninstall()
   f = ram.get_quantization_func("OCTAV", rq.TFLOperationName.FULLY_CONNECTED,
                                 rq.QuantizeMode.MATERIALIZE)
   assert f.args[0].__module__.startswith("ai_edge_quantizer.")
   assert ram.hadamard_rotation.get_tensor_quant_params is ref_had
+  assert ref_tu.pack_data is ref_pack
+  assert ram.get_quantization_func("GPTQ", rq.TFLOperationName.FULLY_CONNECTED,
+                                   rq.QuantizeMode.CALIBRATE) is ram.gptq.calibrate
+  # calibration / pack rebinding are opt-out
+  plugin.install(ram, calibration=False, pack=False)
+  try:
+    assert ram.get_quantization_func("GPTQ", rq.TFLOperationName.FULLY_CONNECTED,
+                                     rq.QuantizeMode.CALIBRATE) is ram.gptq.calibrate
+    assert ref_tu.pack_data is ref_pack
+  finally:
+    plugin.uninstall()
 
 
 def test_plugin_prefetch_walks_the_model_like_the_reference(monkeypatch):

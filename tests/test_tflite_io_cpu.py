@@ -171,7 +171,26 @@ def test_recipe_manager_and_recipes():
   rm2.load_quantization_recipe(rm.get_quantization_recipe())   # JSON round trip
   assert rm2.get_quantization_recipe() == rm.get_quantization_recipe()
   assert not rm.need_calibration()
-  with pytest.raises(ValueError, match="Unregistered algorithm"):
+  with pytest.raises(ValueError, match="Unsupported algorithm key: nope"):  # recipe_manager.py:113-116
     rm.add_quantization_config(".*", Op.FULLY_CONNECTED, algorithm_key="nope")
+  # A `*` entry is resolved per op at lookup: a blockwise recipe leaves CONV_2D / CONV_2D_TRANSPOSE
+  # float (their config check raises, recipe_manager.py:185-198) instead of handing them a
+  # BLOCKWISE_32 config that fails later in the materialiser.
+  rb = recipe_manager.RecipeManager()
+  rb.load_quantization_recipe(recipe.dynamic_wi4b32_afp32())
+  assert rb.get_quantization_configs(Op.FULLY_CONNECTED, "a;")[0] == "min_max_uniform_quantize"
+  assert rb.get_quantization_configs(Op.EMBEDDING_LOOKUP, "a;")[0] == "min_max_uniform_quantize"
+  for op in (Op.CONV_2D, Op.CONV_2D_TRANSPOSE, Op.DEPTHWISE_CONV_2D):
+    alg, cfg = rb.get_quantization_configs(op, "a;")
+    assert alg == "no_quantize" and cfg.weight_tensor_config is None, op
+  assert rb.get_quantization_recipe() == recipe.dynamic_wi4b32_afp32()  # the `*` entry stays one entry
+  # a named op replaces its own entry in place, a later `*` replaces the whole scope
+  rb.add_dynamic_config(".*", Op.FULLY_CONNECTED, 8)
+  assert rb.get_quantization_configs(Op.FULLY_CONNECTED, "a;")[1].weight_tensor_config.num_bits == 8
+  assert len(rb.get_quantization_recipe()) == 2
+  rb.add_dynamic_config(".*", Op.ALL_SUPPORTED, 4)
+  assert len(rb.get_quantization_recipe()) == 1
+  with pytest.raises(ValueError, match="Unsupported op for blockwise quantization"):
+    rb.add_dynamic_config(".*", Op.CONV_2D, 4, qtyping.QuantGranularity.BLOCKWISE_32)
   assert recipe.dynamic_wi4b32_afp32()[0]["op_config"]["weight_tensor_config"]["granularity"] == "BLOCKWISE_32"
   assert recipe.weight_only_wi8_afp32()[0]["op_config"]["explicit_dequantize"] is True

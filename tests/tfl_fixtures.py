@@ -17,8 +17,11 @@ def _fc_options(fused_activation=0, keep_num_dims=False):
   return T.RawTable(vt, tab, 0)
 
 
-def fc_stack(weights, biases=None, share_first_weight_with_last=False, embedding=None, batch=2):
-  """weights: list of [out, in] fp32 arrays chained in -> out; returns ModelT."""
+def fc_stack(weights, biases=None, share_first_weight_with_last=False, embedding=None, batch=2,
+             conv_front=None):
+  """weights: list of [out, in] fp32 arrays chained in -> out; returns ModelT.
+  conv_front: optional [out_ch, kh, kw, in_ch] fp32 CONV_2D weight placed in front of the stack
+  (shapes are not meant to run in an interpreter: only the quantizer walks this graph)."""
   m = T.ModelT(version=3, description=b"aeq_b200 synthetic")
   m.buffers.append(T.BufferT())  # buffer 0 is the empty sentinel
   g = T.SubGraphT(name=b"main")
@@ -45,6 +48,15 @@ def fc_stack(weights, biases=None, share_first_weight_with_last=False, embedding
     table = const(b"embedding/table", embedding, T.TensorType.FLOAT32)
     out = act(b"embedding/out", (batch, embedding.shape[1]))
     g.operators.append(T.OperatorT(opcodeIndex=1, inputs=np.array([cur, table], np.int32),
+                                   outputs=np.array([out], np.int32)))
+    cur = out
+  if conv_front is not None:
+    m.operatorCodes.append(T.OperatorCodeT(deprecatedBuiltinCode=T.BuiltinOperator.CONV_2D,
+                                           builtinCode=T.BuiltinOperator.CONV_2D, version=1))
+    cw = const(b"conv/w", conv_front, T.TensorType.FLOAT32)
+    out = act(b"conv/out", (batch, weights[0].shape[1]))
+    g.operators.append(T.OperatorT(opcodeIndex=len(m.operatorCodes) - 1,
+                                   inputs=np.array([cur, cw, -1], np.int32),
                                    outputs=np.array([out], np.int32)))
     cur = out
   first_w = None
