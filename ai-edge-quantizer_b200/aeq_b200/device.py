@@ -151,6 +151,17 @@ def minmax_tensor(x: torch.Tensor, lo: Optional[float] = None,
   return out
 
 
+def ema_sequence(pairs: torch.Tensor, smoothing: float = 0.95) -> torch.Tensor:
+  """[2] = the calibrator's moving average folded over [n, 2] per-batch (min, max) pairs in batch
+  order (aeqb_ema_sequence_f32; qsv_utils.py:43-68, first batch verbatim)."""
+  if not pairs.is_cuda or pairs.dtype != torch.float32 or pairs.dim() != 2 or pairs.shape[1] != 2:
+    raise ValueError("expected a float32 CUDA tensor of shape [n, 2]")
+  pairs = pairs.contiguous()
+  out = torch.empty(2, dtype=torch.float32, device=pairs.device)
+  _lib.call("aeqb_ema_sequence_f32", _ptr(pairs), pairs.shape[0], float(smoothing), _ptr(out), _stream())
+  return out
+
+
 def row_stats(x: torch.Tensor, want_minmax: bool = True, want_sumsq: bool = False):
   """Per-row (min, max, sum of squares) of a 2-D tensor; absent outputs are None."""
   _check_f32_2d(x)
@@ -274,6 +285,44 @@ def channel_rows_back(y: torch.Tensor, shape, qdim: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ batched (whole model)
+def _rows_jobs(xs, outs):
+  jobs = (_lib.RowsJob * len(xs))()
+  for i, (x, o) in enumerate(zip(xs, outs)):
+    jobs[i] = _lib.RowsJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
+                           _ptr(o.scale), _ptr(o.zero_point))
+  return jobs
+
+
+def _blocks_jobs(xs, outs):
+  jobs = (_lib.BlocksJob * len(xs))()
+  for i, (x, o) in enumerate(zip(xs, outs)):
+    jobs[i] = _lib.BlocksJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
+                             _ptr(o.scale), _ptr(o.scale_f16))
+  return jobs
+
+
+# A steady-state caller (a serving loop, the benchmark) passes the same input list and the same
+# preallocated outputs again and again: the job table of a 477-tensor model is then built once
+# instead of per call.  Keyed by the identity of both lists and checked against the first / last
+# device pointers, so a list that was rebuilt in place is noticed.
+_jobs_cache: dict = {}
+
+
+def _cached_jobs(kind, xs, outs, build):
+  if len(xs) < 32:
+    return build()
+  key = (kind, id(xs), id(outs), len(xs))
+  stamp = (_ptr(xs[0]), _ptr(xs[-1]), tuple(_ptr(t) for t in outs[0]), tuple(_ptr(t) for t in outs[-1]))
+  hit = _jobs_cache.get(key)
+  if hit is not None and hit[0] == stamp:
+    return hit[1]
+  jobs = build()
+  if len(_jobs_cache) > 16:
+    _jobs_cache.clear()
+  _jobs_cache[key] = (stamp, jobs)
+  return jobs
+
+
 def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = True,
                        want_packed: bool = False, outs=None, mirror=None):
   """Per-channel requantisation of many tensors in as few persistent launches as possible.
@@ -296,10 +345,7 @@ def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = Tru
           torch.empty(rows * cols * bits // 8, dtype=torch.uint8, device=dev) if want_packed else None,
           torch.empty((rows, 1), dtype=torch.float32, device=dev),
           torch.empty((rows, 1), dtype=torch.int32, device=dev)))
-  jobs = (_lib.RowsJob * n)()
-  for i, (x, o) in enumerate(zip(xs, outs)):
-    jobs[i] = _lib.RowsJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
-                           _ptr(o.scale), _ptr(o.zero_point))
+  jobs = _cached_jobs("rows", xs, outs, lambda: _rows_jobs(xs, outs))
   if mirror is not None:
     _lib.call("aeqb_requant_rows_batch_mirror_f32", ctypes.cast(jobs, ctypes.c_void_p), n, bits,
               int(symmetric), mirror.deltas_ptr, mirror.n_peers, _stream())
@@ -311,8 +357,12 @@ def requant_rows_batch(xs, bits: int, symmetric: bool = True, want_q: bool = Tru
 
 def requant_blocks_batch(xs, block: int, bits: int, want_q: bool = False,
                          want_packed: bool = True, want_scale: bool = False,
-                         want_scale_f16: bool = True, outs=None):
-  """Blockwise requantisation of many tensors in as few persistent launches as possible."""
+                         want_scale_f16: bool = True, outs=None, mirror=None):
+  """Blockwise requantisation of many tensors in as few persistent launches as possible.
+
+  `mirror` (peer.PeerScales with dtype float16): the `scale_f16` outputs in `outs` are views into
+  `mirror.local`, and the kernel also stores every block's fp16 scale into the other ranks' copies
+  of the gathered buffer (aeqb_requant_blocks_batch_mirror_f32)."""
   import ctypes
   n = len(xs)
   if outs is None:
@@ -332,10 +382,11 @@ def requant_blocks_batch(xs, block: int, bits: int, want_q: bool = False,
           torch.empty((rows, nb), dtype=torch.float32, device=dev) if want_scale else None,
           None,
           torch.empty((rows, nb), dtype=torch.float16, device=dev) if want_scale_f16 else None))
-  jobs = (_lib.BlocksJob * n)()
-  for i, (x, o) in enumerate(zip(xs, outs)):
-    jobs[i] = _lib.BlocksJob(_ptr(x), x.shape[0], x.shape[1], None, _ptr(o.q), _ptr(o.packed),
-                             _ptr(o.scale), _ptr(o.scale_f16))
+  jobs = _cached_jobs("blocks", xs, outs, lambda: _blocks_jobs(xs, outs))
+  if mirror is not None:
+    _lib.call("aeqb_requant_blocks_batch_mirror_f32", ctypes.cast(jobs, ctypes.c_void_p), n, block,
+              bits, mirror.deltas_ptr, mirror.n_peers, _stream())
+    return outs
   _lib.call("aeqb_requant_blocks_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), n, block, bits,
             _stream())
   return outs

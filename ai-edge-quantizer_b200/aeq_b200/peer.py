@@ -27,24 +27,29 @@ from aeq_b200 import _lib
 class _DevMem:
   """__cuda_array_interface__ holder so torch can view a raw device allocation."""
 
-  def __init__(self, ptr: int, n_floats: int):
+  def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
     self.__cuda_array_interface__ = {
-        "shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        "shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+_TYPESTR = {torch.float32: ("<f4", 4), torch.float16: ("<f2", 2)}
 
 
 class PeerScales:
   """`[world, slots]` fp32 on every rank; row r is written by rank r's kernels on all ranks."""
 
-  def __init__(self, slots: int, device: torch.device, group=None):
+  def __init__(self, slots: int, device: torch.device, group=None, dtype: torch.dtype = torch.float32):
+    """dtype: torch.float32 (per-channel scales) or torch.float16 (blockwise scale tensors)."""
     if not (dist.is_available() and dist.is_initialized()):
       raise RuntimeError("PeerScales needs an initialised process group")
     self.group = group
     self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
     if self.world - 1 > 15:
       raise ValueError("at most 16 ranks (kMaxPeers = 15)")
-    self.slots = int(slots)
+    typestr, itemsize = _TYPESTR[dtype]
+    self.slots = (int(slots) * itemsize + 15) // 16 * 16 // itemsize  # every rank's row starts 16-byte aligned
     self.device = device
-    nbytes = self.world * self.slots * 4
+    nbytes = self.world * self.slots * itemsize
     # Every step below ends in a vote, so that a rank whose allocation or mapping failed does not
     # leave the others waiting in a collective: either all ranks get a PeerScales or all raise.
     self._base = None
@@ -77,8 +82,8 @@ class PeerScales:
     self._vote(err, "mapping the peers' buffers")
     self.n_peers = len(deltas)
     self._deltas = (ctypes.c_int64 * max(1, self.n_peers))(*deltas)
-    self.gathered = torch.as_tensor(_DevMem(self._base, self.world * self.slots), device=device).view(
-        self.world, self.slots)
+    self.gathered = torch.as_tensor(_DevMem(self._base, self.world * self.slots, typestr),
+                                    device=device).view(self.world, self.slots)
     self.local = self.gathered[self.rank]  # this rank's scale outputs are views into this row
     self.sync()
 

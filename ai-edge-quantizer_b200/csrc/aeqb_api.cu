@@ -114,10 +114,21 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
 }
 
 int run_blocks(const aeqb::BlocksJob* jobs, int64_t n, int block, int bits, cudaStream_t st,
-               const char* who) {
+               const char* who, const aeqb::PeerMirror* peers = nullptr) {
   const int sms = sm_count();
   aeqb::BlocksBatch b{};
   b.block = block; b.bits = bits;
+  if (peers && peers->n > 0) {  // only the tile-stream kernel mirrors, and only packed + fp16 scale jobs
+    b.peers = *peers;
+    for (int64_t i = 0; i < n; ++i) {
+      const aeqb::BlocksJob& j = jobs[i];
+      if (j.n <= 0) continue;
+      if (!aeqb::blocks_job_streamable(j) || j.q || !j.packed || !j.scale_f16 ||
+          (reinterpret_cast<uintptr_t>(j.scale_f16) & 3))
+        return fail("%s: tensor %lld cannot mirror its scales (needs 16-byte aligned x, packed + fp16 "
+                    "scale outputs only, 4-byte aligned scale_f16)", who, (long long)i);
+    }
+  }
   bool bq = false, bp = false;
   auto flush = [&]() -> int {
     if (b.n_jobs == 0) return 0;
@@ -284,6 +295,38 @@ int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, i
   }
   return run_blocks(v.data(), n_jobs, block, bits, static_cast<cudaStream_t>(stream),
                     "aeqb_requant_blocks_batch_f32");
+}
+
+int aeqb_requant_blocks_batch_mirror_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block,
+                                         int bits, const int64_t* peer_delta_bytes, int n_peers,
+                                         void* stream) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad job list");
+  if (n_peers < 0 || n_peers > aeqb::kMaxPeers || (n_peers > 0 && !peer_delta_bytes))
+    return fail("bad peer list (0..%d peers)", aeqb::kMaxPeers);
+  aeqb::PeerMirror pm{};
+  pm.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) {
+    if (peer_delta_bytes[i] % 4) return fail("peer offset %d is not a multiple of 4 bytes", i);
+    pm.delta[i] = peer_delta_bytes[i];
+  }
+  std::vector<aeqb::BlocksJob> v(static_cast<size_t>(n_jobs));
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const aeqb_blocks_job& a = jobs[i];
+    if (int rc = blocks_args_ok(a.rows, a.cols, block, bits, a.packed, a.x)) return rc;
+    aeqb::BlocksJob j{};
+    j.x = a.x; j.q = a.q; j.packed = a.packed; j.scale = a.scale; j.scale_f16 = a.scale_f16;
+    j.clip = a.clip; j.n = a.rows * a.cols;
+    v[static_cast<size_t>(i)] = j;
+  }
+  return run_blocks(v.data(), n_jobs, block, bits, static_cast<cudaStream_t>(stream),
+                    "aeqb_requant_blocks_batch_mirror_f32", &pm);
+}
+
+int aeqb_ema_sequence_f32(const float* pairs, int64_t n, float smoothing, float* out2, void* stream) {
+  if (n < 0) return fail("negative batch count");
+  if (!out2 || (n > 0 && !pairs)) return fail("pairs / out2 are NULL");
+  return check(aeqb::launch_ema_sequence(pairs, n, smoothing, out2, static_cast<cudaStream_t>(stream)),
+               "aeqb_ema_sequence_f32");
 }
 
 size_t aeqb_minmax_workspace_bytes(void) { return aeqb::minmax_workspace_bytes(); }

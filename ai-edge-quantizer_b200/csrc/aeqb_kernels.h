@@ -85,6 +85,7 @@ struct BlocksBatch {
   int block;
   int bits;
   long long n_tiles;
+  PeerMirror peers;  // n > 0: the fp16 scales are also stored into the peers' gathered buffers
 };
 long long blocks_job_tiles(long long n);
 bool blocks_job_streamable(const BlocksJob& j);
@@ -115,6 +116,9 @@ cudaError_t launch_row_stats(const float* x, long long rows, int cols, float* mn
 cudaError_t launch_block_minmax(const float* x, long long n, int block, float* mn, float* mx,
                                 cudaStream_t st);
 
+// qsv_utils.moving_average_update folded over n (min, max) pairs in batch order (reduce.cu).
+cudaError_t launch_ema_sequence(const float* pairs, long long n, float smoothing, float* out2,
+                                cudaStream_t st);
 cudaError_t launch_hist(const float* x, long long n, float lb, float bw, int nbins, int finite_only,
                         long long* counts, int sm_count, cudaStream_t st);
 size_t mse_workspace_bytes();

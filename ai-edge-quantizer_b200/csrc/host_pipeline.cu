@@ -25,11 +25,13 @@
 // workers.  The default is the current device only — under one-process-per-GPU
 // launchers every rank sees every GPU and must not spill onto its neighbours'.
 #include <ctype.h>
+#include <immintrin.h>
 #include <pthread.h>
 #include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -63,6 +65,56 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// ---------------------------------------------------------------- the copy itself
+// Both staging directions write memory the CPU will not read again (pinned staging is read by
+// the DMA engine, results by the caller much later), so the stores bypass the cache: a cached
+// store first READS the destination line (read-for-ownership), i.e. 3 bytes of DRAM traffic per
+// byte copied instead of 2 — and DRAM traffic is what bounds sixteen workers.  glibc's memcpy
+// only switches to streaming stores far above the 2 MiB pieces used here.
+__attribute__((target("avx2"))) void copy_stream_avx2(char* dst, const char* src, size_t n) {
+  const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head >= n) { memcpy(dst, src, n); return; }
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
+bool use_stream_copy() {
+  static const bool on = env_int("AEQB_HOST_NT", 1) != 0 && __builtin_cpu_supports("avx2");
+  return on;
+}
+
+inline void copy_bytes(void* dst, const void* src, size_t n) {
+  if (n >= 4096 && use_stream_copy())
+    copy_stream_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n);
+  else
+    memcpy(dst, src, n);
+}
+
+// Fresh NumPy outputs are untouched anonymous memory: with 4 KiB pages the copy-out spends more
+// time in page faults than in copying.  Where transparent huge pages are available on request
+// (THP "madvise" or "always") the 2 MiB-aligned interior of a large output is faulted 2 MiB at
+// a time instead.  Advisory: failures are ignored.
+void advise_huge(void* p, size_t bytes) {
+  static const bool on = env_int("AEQB_HOST_THP", 1) != 0;
+  if (!on || !p || bytes < (8u << 20)) return;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + (2u << 20) - 1) & ~uintptr_t((2u << 20) - 1);
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~uintptr_t((2u << 20) - 1);
+  if (e > a) madvise(reinterpret_cast<void*>(a), e - a, MADV_HUGEPAGE);
+}
+
 // ---------------------------------------------------------------- worker pool
 // A counter the submitter can wait on: "all copy tasks of this chunk are done".
 struct Latch {
@@ -80,7 +132,21 @@ struct Latch {
   }
 };
 
-struct CopyTask { void* dst; const void* src; size_t bytes; Latch* latch; };
+struct CopyTask { void* dst; const void* src; size_t bytes; Latch* latch; bool populate; };
+
+// Sources are often views of an mmap'd model file: mapping its page-cache pages one fault at a
+// time costs more than copying them.  MADV_POPULATE_READ (Linux 5.14+) maps a whole piece in one
+// call; on older kernels or odd mappings it fails and the copy faults the pages as before.
+#ifndef MADV_POPULATE_READ
+#define MADV_POPULATE_READ 22
+#endif
+inline void populate_source(const void* src, size_t bytes) {
+  static const bool on = env_int("AEQB_HOST_POPULATE", 1) != 0;
+  if (!on) return;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(4095);
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(src) + bytes + 4095) & ~uintptr_t(4095);
+  madvise(reinterpret_cast<void*>(a), e - a, MADV_POPULATE_READ);
+}
 
 class Pool {
  public:
@@ -96,7 +162,7 @@ class Pool {
     for (auto& t : threads_) t.join();
   }
   // Splits one copy into kPieceBytes pieces (64-byte aligned cuts) and queues them.
-  void copy(void* dst, const void* src, size_t bytes, Latch* latch) {
+  void copy(void* dst, const void* src, size_t bytes, Latch* latch, bool populate = false) {
     if (bytes == 0) return;
     const size_t pieces = (bytes + kPieceBytes - 1) / kPieceBytes;
     latch->add(static_cast<int>(pieces));
@@ -105,7 +171,7 @@ class Pool {
       for (size_t p = 0; p < pieces; ++p) {
         const size_t off = p * kPieceBytes;
         q_.push_back({static_cast<char*>(dst) + off, static_cast<const char*>(src) + off,
-                      std::min(kPieceBytes, bytes - off), latch});
+                      std::min(kPieceBytes, bytes - off), latch, populate});
       }
     }
     cv_.notify_all();
@@ -129,7 +195,8 @@ class Pool {
         t = q_.front();
         q_.pop_front();
       }
-      memcpy(t.dst, t.src, t.bytes);
+      if (t.populate) populate_source(t.src, t.bytes);
+      copy_bytes(t.dst, t.src, t.bytes);
       t.latch->done();
     }
   }
@@ -209,7 +276,7 @@ int ring_init(Ring& r, int dev) {
   const std::vector<int> cpus = local_cpus(dev);
   int hw = static_cast<int>(cpus.empty() ? std::thread::hardware_concurrency() : cpus.size());
   if (hw <= 0) hw = 4;
-  const int n_threads = std::max(1, std::min(env_int("AEQB_HOST_THREADS", 8), hw));
+  const int n_threads = std::max(1, std::min(env_int("AEQB_HOST_THREADS", 16), hw));
   r.pool.reset(new Pool(n_threads, env_int("AEQB_HOST_NO_BIND", 0) ? std::vector<int>() : cpus));
   for (Slot& s : r.slots) {
     if (int rc = aeqb::host_check(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
@@ -425,6 +492,8 @@ int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, i
     c.in_pinned = is_pinned(hj.x);
     c.q_pinned = is_pinned(hj.q); c.p_pinned = is_pinned(hj.packed);
     c.s_pinned = is_pinned(hj.scale); c.z_pinned = is_pinned(hj.zp); c.f_pinned = is_pinned(hj.f16);
+    if (!c.q_pinned) advise_huge(hj.q, static_cast<size_t>(hj.rows * hj.cols));
+    if (!c.p_pinned) advise_huge(hj.packed, static_cast<size_t>(hj.rows * hj.cols) * bits / 8);
     for (long long r0 = 0; r0 < hj.rows; r0 += chunk_rows) {
       c.r0 = r0;
       c.nr = std::min(chunk_rows, hj.rows - r0);
@@ -447,7 +516,7 @@ int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, i
     const bool need_stage = !(c.in_pinned && c.q_pinned && c.p_pinned && c.s_pinned && c.z_pinned && c.f_pinned);
     if (need_stage) { if (int rc = ensure_staging(r, s)) return rc; }
     if (!c.in_pinned)
-      r.pool->copy(s.h_in, c.job->x + c.r0 * c.job->cols, static_cast<size_t>(c.nr * c.job->cols) * 4, &s.staged_in);
+      r.pool->copy(s.h_in, c.job->x + c.r0 * c.job->cols, static_cast<size_t>(c.nr * c.job->cols) * 4, &s.staged_in, true);
     c.staged = true;
     return 0;
   };
@@ -507,7 +576,7 @@ int copy_in_locked(void* dst_dev, const void* src, size_t bytes, cudaStream_t us
     s.copied_out.wait();
     if (s.stream && cudaStreamSynchronize(s.stream) != cudaSuccess) return aeqb::host_fail("stream synchronise failed");
     const size_t off = k * kCopyPiece;
-    r->pool->copy(s.h_in, static_cast<const char*>(src) + off, std::min(kCopyPiece, bytes - off), &s.staged_in);
+    r->pool->copy(s.h_in, static_cast<const char*>(src) + off, std::min(kCopyPiece, bytes - off), &s.staged_in, true);
     return 0;
   };
   for (size_t k = 0; k < n && !rc; ++k) {
@@ -539,12 +608,15 @@ int copy_out_locked(void* dst, const void* src_dev, size_t bytes, cudaStream_t u
   Ring* r = nullptr;
   if (int rc = ring_for(dev, &r)) return rc;
   if (int rc = aeqb::host_check(cudaSetDevice(dev), "cudaSetDevice")) return rc;
+  advise_huge(dst, bytes);
   const size_t piece = std::min(kCopyPiece, kOutStage & ~size_t(255));
   const size_t n = (bytes + piece - 1) / piece;
+  std::vector<Slot*> slot_of(n, nullptr);
   int rc = 0;
   for (size_t k = 0; k < n && !rc; ++k) {
     Slot& s = r->slots[r->next];
     r->next = (r->next + 1) % kSlots;
+    slot_of[k] = &s;
     if ((rc = slot_retire(*r, s))) break;
     if ((rc = ensure_staging(*r, s))) break;
     s.copied_out.wait();
@@ -554,6 +626,9 @@ int copy_out_locked(void* dst, const void* src_dev, size_t bytes, cudaStream_t u
                                           cudaMemcpyDeviceToHost, s.stream), "D2H");
     if (!rc) rc = aeqb::host_check(cudaEventRecord(s.done, s.stream), "cudaEventRecord");
     if (!rc) s.in_flight = true;
+    // hand the piece issued two steps ago to the workers now, so that its copy runs under the
+    // downloads that follow instead of when its slot comes round again
+    if (!rc && k >= 2) rc = slot_retire(*r, *slot_of[k - 2]);
   }
   if (!rc)
     for (Slot& s : r->slots)

@@ -461,4 +461,32 @@ cudaError_t launch_block_minmax(const float* x, long long n, int block, float* m
   return count_launch();
 }
 
+// ---------------------------------------------------------------- EMA over calibration batches
+// out2 = fold of qsv_utils.moving_average_update (utils/qsv_utils.py:43-68) over n per-batch
+// (min, max) pairs IN BATCH ORDER: the first pair is kept verbatim (calibrator.py:415-416), then
+// old = fl32(fl32(s * old) + fl32(c * new)) with s = fl32(smoothing) and c = fl32(1 - smoothing
+// evaluated in float64) — NumPy 2 keeps an fp32 array fp32 against the Python-float weak
+// scalars.  The recurrence is inherently serial (O(1) per batch), so one thread walks it; the
+// multiply and add are kept apart (no FMA contraction) to round exactly like NumPy.
+__global__ void ema_sequence_kernel(const float* __restrict__ pairs, long long n, float s, float c,
+                                    float* __restrict__ out2) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (n <= 0) return;
+  float mn = pairs[0], mx = pairs[1];
+  for (long long i = 1; i < n; ++i) {
+    mn = __fadd_rn(__fmul_rn(s, mn), __fmul_rn(c, pairs[2 * i]));
+    mx = __fadd_rn(__fmul_rn(s, mx), __fmul_rn(c, pairs[2 * i + 1]));
+  }
+  out2[0] = mn;
+  out2[1] = mx;
+}
+
+cudaError_t launch_ema_sequence(const float* pairs, long long n, float smoothing, float* out2,
+                                cudaStream_t st) {
+  const float s = smoothing;
+  const float c = static_cast<float>(1.0 - static_cast<double>(smoothing));
+  ema_sequence_kernel<<<1, 32, 0, st>>>(pairs, n, s, c, out2);
+  return count_launch();
+}
+
 }  // namespace aeqb

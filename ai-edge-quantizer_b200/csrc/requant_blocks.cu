@@ -66,14 +66,24 @@ __device__ __forceinline__ float group_max_nan(float v) {
   return v;
 }
 
-template <int BLOCK, bool OUT_Q, bool OUT_P>
+// MIRROR: the fp16 scales of a sharded job set also go to the other ranks' copies of the gathered
+// scale buffer (NVLink peer memory, `b.peers`), which is the all-gather of blockwise scales
+// (2 B per 32 weights, the one exchange of a blockwise model: quantize_tensor.py:107-147 needs
+// every tensor's scales to serialise it) without a collective launch.  To make those remote
+// stores worth their NVLink packets a warp then takes CONTIGUOUS slices of the tile, parks its
+// scales in a private shared-memory strip and sends the strip to every peer as one run of
+// coalesced 4-byte stores (64 B per peer and tile for block 32) instead of 2 bytes at a time.
+template <int BLOCK, bool OUT_Q, bool OUT_P, bool MIRROR>
 __global__ void __launch_bounds__((kNW + 1) * 32, 2)
     requant_blocks_stream(const __grid_constant__ BlocksBatch b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ StageDesc desc[kStages];
+  __shared__ __align__(16) uint16_t strip[MIRROR ? kNW : 1][MIRROR ? (kStageFloats / BLOCK / kNW) : 1];
   constexpr int LPB = BLOCK / 8;
+  constexpr int kSliceBlocks = kSlice / BLOCK;               // scales one slice produces
+  constexpr int kSlicesPerWarp = kStageFloats / kSlice / kNW;  // contiguous split of a full tile
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
@@ -139,7 +149,9 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
     const bool w_f16 = leader && hp != nullptr;
     const int nslices = (ne + kSlice - 1) / kSlice;
 
-    for (int sl = warp; sl < nslices; sl += kNW) {
+    const int sl_first = MIRROR ? warp * kSlicesPerWarp : warp;
+    const int sl_last = MIRROR ? min(nslices, sl_first + kSlicesPerWarp) : nslices;
+    for (int sl = sl_first; sl < sl_last; sl += (MIRROR ? 1 : kNW)) {
       const int f0 = sl * kSlice + lane * 8;  // first float of this lane inside the tile
       const bool valid = f0 < ne;             // whole blocks are valid or not (ne % BLOCK == 0)
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
@@ -203,9 +215,32 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
       if (OUT_P) *reinterpret_cast<uint32_t*>(pp + (f0 >> 1)) = word_p;
       if (w_scale) sp[blk0 + blk] = scale;
       if (w_f16) hp[blk0 + blk] = h16;
+      if (MIRROR && leader) strip[warp][blk - sl_first * kSliceBlocks] = h16;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // the tile is consumed; the strip is this warp's own
+    if (MIRROR && hp != nullptr) {
+      const int b_first = sl_first * kSliceBlocks;
+      const int nb = min(ne / BLOCK, b_first + kSlicesPerWarp * kSliceBlocks) - b_first;  // scales in the strip
+      if (nb > 0) {
+        uint16_t* dst0 = hp + blk0 + b_first;
+        const int np = b.peers.n;
+        if ((nb & 1) == 0 && (reinterpret_cast<uintptr_t>(dst0) & 3) == 0) {
+          const int words = nb >> 1;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(strip[warp]);
+          for (int i = lane; i < np * words; i += 32) {
+            const int p = i / words, wd = i - p * words;
+            reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dst0) + b.peers.delta[p])[wd] = src[wd];
+          }
+        } else {
+          for (int i = lane; i < np * nb; i += 32) {
+            const int p = i / nb, k = i - p * nb;
+            reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(dst0) + b.peers.delta[p])[k] = strip[warp][k];
+          }
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -239,9 +274,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int BLOCK, bool OUT_Q, bool OUT_P>
+template <int BLOCK, bool OUT_Q, bool OUT_P, bool MIRROR = false>
 cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
-  auto kern = requant_blocks_stream<BLOCK, OUT_Q, OUT_P>;
+  auto kern = requant_blocks_stream<BLOCK, OUT_Q, OUT_P, MIRROR>;
   const int smem = kStages * kStageBytes;
   static bool configured = false;
   if (!configured) {
@@ -258,6 +293,10 @@ cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
 template <int BLOCK>
 cudaError_t launch_stream_out(const BlocksBatch& b, bool out_q, bool out_p, int sm_count,
                               cudaStream_t st) {
+  if (b.peers.n > 0) {  // sharded model: packed payload stays local, fp16 scales reach every rank
+    if (out_q || !out_p) return cudaErrorInvalidValue;
+    return launch_stream<BLOCK, false, true, true>(b, sm_count, st);
+  }
   if (out_q && out_p) return launch_stream<BLOCK, true, true>(b, sm_count, st);
   if (out_p) return launch_stream<BLOCK, false, true>(b, sm_count, st);
   if (out_q) return launch_stream<BLOCK, true, false>(b, sm_count, st);

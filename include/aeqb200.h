@@ -125,6 +125,15 @@ AEQB_API int aeqb_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t 
 AEQB_API int aeqb_requant_rows_batch_mirror_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits,
                                                 int symmetric, const int64_t* peer_delta_bytes,
                                                 int n_peers, void* stream);
+/* The blockwise form: every block's fp16 scale (2 B per `block` weights — the scale tensor
+ * quantize_tensor._perform_blockwise_quantization stores, transformations/quantize_tensor.py:107-147)
+ * is also stored into `n_peers` peer mappings of the gathered fp16 scale buffer, 64 B per peer and
+ * 32 KiB tile as coalesced 4-byte stores.  Jobs must have packed + scale_f16 outputs only
+ * (q == NULL: quantised payloads stay on the owning GPU), `scale_f16` pointing into the local copy. */
+AEQB_API int aeqb_requant_blocks_batch_mirror_f32(const aeqb_blocks_job* jobs, int64_t n_jobs,
+                                                  int block, int bits,
+                                                  const int64_t* peer_delta_bytes, int n_peers,
+                                                  void* stream);
 /* A device buffer other processes on the node can map (CUDA IPC): `handle64` receives 64 opaque
  * bytes to send to the peers, which call aeqb_peer_open on them. */
 AEQB_API int aeqb_peer_alloc(size_t bytes, void** ptr, void* handle64);
@@ -190,6 +199,13 @@ AEQB_API int aeqb_minmax_tensors_f32(const aeqb_minmax_job* jobs, int64_t n_jobs
                                      int use_lo, int use_hi, void* ws, void* stream);
 AEQB_API int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float hi, int use_lo,
                                     int use_hi, float* out2, void* ws, void* stream);
+
+/* out2 = qsv_utils.moving_average_update (utils/qsv_utils.py:43-68) folded over n per-batch
+ * (min, max) pairs in batch order: the first pair verbatim (calibrator.py:415-416), then
+ * smoothing * old + (1 - smoothing) * new in fp32 with NumPy's weak-scalar rounding.  pairs:
+ * DEVICE [n, 2] (e.g. the all-gathered output of aeqb_minmax_tensors_f32), out2: DEVICE [2]. */
+AEQB_API int aeqb_ema_sequence_f32(const float* pairs, int64_t n, float smoothing, float* out2,
+                                   void* stream);
 
 /* counts[clip(int32(floor((x - lower_bound) / bin_width)), 0, nbins - 1)] += 1 for every element
  * (finite ones only when finite_only != 0): the bin-count step of

@@ -441,6 +441,33 @@ def gptq_requant(w, hessian, bits: int, symmetric: bool = True, block: int = 0,
               q=gptq_quantize(w, scale, zp, hinv, bits, symmetric, block))
 
 
+def hadamard_rotate_hessian(hessian, n: int):
+  """R^T H R in float64 for the block-diagonal R = diag(H_n / sqrt(n), ...) that
+  `hadamard_rotate` applies to the weight's last axis.  No reference function computes this: it
+  follows from the two it composes — the runtime feeds the rotated op x R (the activation-side
+  INSERT_HADAMARD_ROTATION, hadamard_rotation.py:206-283), and gptq.calibrate's Hessian of x R is
+  (2 / n_s) (X R)^T (X R) = R^T H R (gptq.py:100-106)."""
+  h = np.asarray(hessian, dtype=np.float64)
+  k = h.shape[0]
+  if n <= 1:
+    return h.copy()
+  r = hadamard_matrix(n).astype(np.float64)
+  out = h.reshape(k // n, n, k // n, n)
+  out = np.einsum("ab,ibjc,cd->iajd", r.T, out, r, optimize=True)
+  return out.reshape(k, k)
+
+
+def hadamard_gptq_requant(w, hessian, bits: int, max_size: int | None = None, symmetric: bool = True):
+  """BASELINE.json configs[4] as one algorithm: rotate W (hadamard_rotation.py:93-134), rotate the
+  Hessian with the same R, then GPTQ on the pair (gptq.py:219-300: min/max scales of the ROTATED
+  weight, damped inverse, OBS loop).  Each stage is the pinned oracle of its reference function."""
+  rot, n = hadamard_rotate(w, max_size)
+  h_rot = hadamard_rotate_hessian(hessian, n)
+  out = gptq_requant(rot, h_rot, bits, symmetric)
+  out.update(hadamard_size=n, random_binary_vector=np.ones(n, np.int8), rotated=rot, hessian_rotated=h_rot)
+  return out
+
+
 # --------------------------------------------------------------------------
 # §8(f) row 3: dequantized_weight_recovery / float_casting
 # --------------------------------------------------------------------------

@@ -355,3 +355,56 @@ def test_gptq_larger_proxy_loss(cuda):
   assert (d > 0).mean() <= 2e-2, (d > 0).mean()
   assert loss(r.quantized_data) <= loss(ref["q"]) * 1.001
   assert loss(r.quantized_data) < 0.97 * loss(plain["q"])
+
+
+def test_hadamard_rotated_hessian(cuda):
+  """R^T H R on the device (two passes of the rotation kernel around a transpose) against the
+  oracle's float64 einsum, and against the definition: the Hessian of the rotated activations."""
+  import torch
+  from aeq_b200.algorithms.uniform_quantize import hadamard_gptq
+  for k, n in ((256, 256), (768, 256), (512, 64), (96, 32), (48, 16)):
+    x = O.synthetic_activation((3, 200, k), k)
+    x *= (1.0 + np.arange(k, dtype=np.float32) % 5)
+    h = O.gptq_hessian(x)
+    want = O.hadamard_rotate_hessian(h, n)
+    got = hadamard_gptq.rotate_hessian_device(torch.from_numpy(h).to(cuda), n).cpu().numpy()
+    assert got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 * np.abs(np.diag(want)).max())
+    xr, n2 = O.hadamard_rotate(x, n)
+    assert n2 == n
+    np.testing.assert_allclose(O.gptq_hessian(xr), want, rtol=0, atol=2e-5 * np.abs(np.diag(want)).max())
+
+
+@pytest.mark.parametrize("rows,k,max_size", [(64, 256, None), (96, 768, None), (40, 512, 64)])
+def test_hadamard_gptq_matches_composed_oracle(cuda, rows, k, max_size):
+  """BASELINE.json configs[4] as one algorithm: rotated weight, rotated Hessian, GPTQ.  Scales are
+  min/max of the rotated weight (<= 1e-6 rel.: the rotation's summation order), integers within
+  GPTQ's bars (a flipped rounding decision propagates along its row), proxy loss within 0.1 %."""
+  from aeq_b200 import qtyping
+  from aeq_b200.algorithms.uniform_quantize import hadamard_gptq
+  w = O.synthetic_weight(rows, k, rows + k)
+  x = O.synthetic_activation((4, 2 * k, k), k)
+  x = x + 0.5 * np.roll(x, 1, axis=-1)  # correlated input features: GPTQ has something to do
+  h = O.gptq_hessian(x)
+  cfg = qtyping.TensorQuantizationConfig(4, True, qtyping.QuantGranularity.CHANNELWISE,
+                                         algorithm_params={"max_hadamard_size": max_size} if max_size else {})
+  r = hadamard_gptq.get_tensor_quant_params(_op_info(w, cfg), cfg, w,
+                                            {"activation_tensor_qsv": {"hessian": h.copy(), "num_samples": 4}})
+  ref = O.hadamard_gptq_requant(w, h.copy(), 4, max_size)
+  assert r.hadamard.hadamard_size == ref["hadamard_size"]
+  np.testing.assert_array_equal(r.hadamard.random_binary_vector, ref["random_binary_vector"])
+  assert r.quantized_dimension == 0 and r.quantized_data.dtype == np.int8 and r.scale.shape == (rows, 1)
+  np.testing.assert_allclose(r.scale, ref["scale"], rtol=2e-6)
+  d = np.abs(r.quantized_data.astype(int) - ref["q"].astype(int))
+  assert (d > 0).mean() <= 2e-2 and d.max() <= 2, ((d > 0).mean(), d.max())
+
+  def loss(q, scale):
+    e = (ref["rotated"] - q.astype(np.float32) * scale).astype(np.float64)
+    return float(np.einsum("ri,ij,rj->", e, ref["hessian_rotated"], e))
+
+  assert abs(loss(r.quantized_data, r.scale) - loss(ref["q"], ref["scale"])) <= 1e-3 * loss(ref["q"], ref["scale"])
+  plain = O.minmax_requant(ref["rotated"], 4)
+  assert loss(r.quantized_data, r.scale) < loss(plain["q"], plain["scale"])
+  # without a Hessian the weight keeps GPTQ's behaviour: parameters only
+  r0 = hadamard_gptq.get_tensor_quant_params(_op_info(w, cfg), cfg, w, None)
+  assert r0.quantized_data is None

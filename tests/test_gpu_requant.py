@@ -193,3 +193,47 @@ def test_peer_buffer_alloc_free(cuda):
   _lib.call("aeqb_peer_free", ptr)
   with pytest.raises(_lib.AeqbError):
     _lib.call("aeqb_peer_alloc", 0, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block", [32, 64, 128, 256])
+def test_block_scales_mirrored_into_peer_copies(cuda, block):
+  """aeqb_requant_blocks_batch_mirror_f32: every block's fp16 scale lands at the same offset of
+  each peer mapping of the gathered buffer (here two more rows of one local buffer; the kernel only
+  sees byte offsets).  Ragged tensors: full tiles, a partial last tile, a partial last slice, an
+  odd number of scales per warp strip."""
+  import ctypes
+  import types
+  import torch
+  from aeq_b200 import _lib, device
+  shapes = [(64, 4096), (24, 11008 // 256 * 256), (3, 2048), (5, 1280), (1, 256), (130, 256)]
+  ws = [_special(O.synthetic_weight(r, c, index=80 + i)) for i, (r, c) in enumerate(shapes)]
+  xs = [_dev(w, cuda) for w in ws]
+  counts = [w.size // block for w in ws]
+  offs = np.concatenate([[0], np.cumsum([(n + 7) // 8 * 8 for n in counts])])  # 16-byte aligned starts
+  buf = torch.full((3, int(offs[-1])), -1.0, dtype=torch.float16, device=cuda)
+  deltas = (ctypes.c_int64 * 2)(buf[1].data_ptr() - buf[0].data_ptr(), buf[2].data_ptr() - buf[0].data_ptr())
+  mirror = types.SimpleNamespace(deltas_ptr=ctypes.cast(deltas, ctypes.c_void_p), n_peers=2)
+  outs = []
+  for w, n, o in zip(ws, counts, offs[:-1]):
+    outs.append(device.Requantized(None, torch.empty(w.size // 2, dtype=torch.uint8, device=cuda), None, None,
+                                   buf[0, int(o):int(o) + n].view(w.shape[0], -1)))
+  device.requant_blocks_batch(xs, block, 4, outs=outs, mirror=mirror)
+  torch.cuda.synchronize()
+  got = buf.cpu().numpy()
+  for w, n, o, out in zip(ws, counts, offs[:-1], outs):
+    ref = O.minmax_requant(w, 4, True, block=block)
+    want = O.blockwise_scale_fp16(ref["scale"]).reshape(-1)
+    for k in range(3):
+      np.testing.assert_array_equal(got[k, int(o):int(o) + n].view(np.uint16), want.view(np.uint16))
+    np.testing.assert_array_equal(out.packed.cpu().numpy(), O.pack_bits(4, ref["q"]))
+  # padding between tensors was not touched on any copy
+  pad = np.ones(int(offs[-1]), bool)
+  for n, o in zip(counts, offs[:-1]):
+    pad[int(o):int(o) + n] = False
+  assert (got[:, pad] == -1.0).all()
+  # a job that also wants the one-value-per-byte integers cannot be mirrored: loud error
+  bad = [device.Requantized(torch.empty(ws[0].shape, dtype=torch.int8, device=cuda), outs[0].packed, None, None,
+                            outs[0].scale_f16)]
+  with pytest.raises(_lib.AeqbError, match="cannot mirror"):
+    device.requant_blocks_batch(xs[:1], block, 4, outs=bad, mirror=mirror)

@@ -162,3 +162,28 @@ def test_minmax_tensors_batched(cuda):
   for a, g in zip(arrs, raw):
     with np.errstate(all="ignore"):
       np.testing.assert_array_equal(g, np.array([a.min(), a.max()], np.float32))
+
+
+def test_ema_sequence_matches_the_calibrator_fold(cuda):
+  """aeqb_ema_sequence_f32 == qsv_utils.moving_average_update folded in batch order, bit-exact
+  (first batch verbatim, fp32 weak-scalar arithmetic, no FMA contraction)."""
+  import torch
+  from aeq_b200 import device
+  rng = np.random.default_rng(12)
+  for n in (1, 2, 7, 512):
+    mins = (-rng.random(n, dtype=np.float32) * 5 - 0.1).astype(np.float32)
+    maxs = (rng.random(n, dtype=np.float32) * 7 + 0.1).astype(np.float32)
+    want = O.ema_sequence([np.full((1, 1, 1), m, np.float32) for m in mins],
+                          [np.full((1, 1, 1), m, np.float32) for m in maxs])
+    pairs = torch.from_numpy(np.stack([mins, maxs], axis=1)).to(cuda)
+    got = device.ema_sequence(pairs).cpu().numpy()
+    assert got[0] == want[0].item() and got[1] == want[1].item(), (n, got, want)
+  # end to end: per-batch filtered min / max of activation batches, then the fold
+  acts = [O.synthetic_activation((4, 64, 256), 40 + i) * (1 + i) for i in range(9)]
+  acts[3][0, 0, 0] = -3.3e38  # filtered by the (-3e38, 3e38) window
+  mm = device.minmax_tensors([torch.from_numpy(a).to(cuda) for a in acts], -3e38, 3e38)
+  got = device.ema_sequence(mm).cpu().numpy()
+  q = {}
+  for a in acts:
+    q = O.ema_update(q, O.activation_qsv(a))
+  assert got[0] == q["min"].item() and got[1] == q["max"].item()
