@@ -45,7 +45,7 @@ SIGNATURES = {
     "aeqb_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I, _P]),
     "aeqb_requant_rows_batch_mirror_f32": (_I, [_P, _L, _I, _I, _P, _I, _P]),
     "aeqb_requant_blocks_batch_mirror_f32": (_I, [_P, _L, _I, _I, _P, _I, _P]),
-    "aeqb_ema_sequence_f32": (_I, [_P, _L, _F, _P, _P]),
+    "aeqb_ema_sequence_f32": (_I, [_P, _L, _D, _P, _P]),
     "aeqb_peer_alloc": (_I, [_c.c_size_t, _P, _P]),
     "aeqb_peer_open": (_I, [_P, _P]),
     "aeqb_peer_close": (_I, [_P]),

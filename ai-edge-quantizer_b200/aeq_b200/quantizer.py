@@ -64,6 +64,8 @@ class Quantizer:
 
   def __init__(self, float_model: Union[str, pathlib.Path, bytes, bytearray, memoryview],
                quantization_recipe=None):
+    import time
+    t0 = time.perf_counter()
     if isinstance(float_model, (str, pathlib.Path)):
       self._float_model = fu.read_model(str(float_model))
       self._float_size = os.path.getsize(float_model)
@@ -75,6 +77,8 @@ class Quantizer:
       self.load_quantization_recipe(quantization_recipe)
     self._result = QuantizationResult([{}], None)
     self.prefetch_stats: dict = {}
+    self.read_seconds = time.perf_counter() - t0
+    self.timings: dict = {}
 
   # ---- recipe
   def load_quantization_recipe(self, recipe) -> None:
@@ -187,8 +191,15 @@ class Quantizer:
     """`external_buffers`: None = automatic (payloads of 2 GB and more leave the flatbuffer)."""
     if not self.get_quantization_recipe():
       raise RuntimeError("Can not quantize without a quantization recipe.")
-    self._apply(self._generate_params(calibration_result))
+    import time
+    t0 = time.perf_counter()
+    params = self._generate_params(calibration_result)
+    t1 = time.perf_counter()
+    self._apply(params)
+    t2 = time.perf_counter()
     data = tfl_model.write_model_to_bytes(self._float_model, external_buffers)
+    self.timings = {"quantization_parameters": t1 - t0, "transformations": t2 - t1,
+                    "serialisation": time.perf_counter() - t2}
     if serialize_to_path is not None:
       with open(serialize_to_path, "wb") as f:
         f.write(data)

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/aeqb200.h"
@@ -66,6 +67,55 @@ int64_t aeqb_launch_count(void) { return aeqb::g_launches.load(); }
 // ---- shared batching logic --------------------------------------------------
 namespace {
 
+// ---- device job tables -----------------------------------------------------------------------
+// More than kMaxInlineJobs tensors of one kernel class go out as ONE persistent launch whose job
+// table lives in device memory.  The table is staged in a small ring of pinned host buffers (a
+// slot is reused only after the copy that read it has completed) and copied on the caller's
+// stream into a stream-ordered allocation that is freed, again in stream order, behind the
+// kernel — so the call stays asynchronous and nothing outlives it.
+struct TableRing {
+  static constexpr int kSlots = 8;
+  void* host[kSlots] = {};
+  size_t cap[kSlots] = {};
+  cudaEvent_t ev[kSlots] = {};
+  bool used[kSlots] = {};
+  int next = 0;
+};
+std::mutex g_table_mu;
+TableRing g_table_ring[64];
+
+bool use_job_tables() {
+  static const bool on = !(getenv("AEQB_NO_JOB_TABLE") && atoi(getenv("AEQB_NO_JOB_TABLE")));
+  return on;
+}
+
+int upload_table(const void* src, size_t bytes, cudaStream_t st, void** d_table) {
+  int dev = 0;
+  if (int rc = check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_table_mu);
+  TableRing& r = g_table_ring[dev];
+  const int i = r.next;
+  r.next = (r.next + 1) % TableRing::kSlots;
+  if (!r.ev[i]) { if (int rc = check(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming), "cudaEventCreate")) return rc; }
+  if (r.used[i]) { if (int rc = check(cudaEventSynchronize(r.ev[i]), "cudaEventSynchronize")) return rc; }
+  if (r.cap[i] < bytes) {
+    if (r.host[i]) cudaFreeHost(r.host[i]);
+    r.host[i] = nullptr; r.cap[i] = 0;
+    const size_t want = (bytes + 65535) & ~size_t(65535);
+    if (int rc = check(cudaHostAlloc(&r.host[i], want, cudaHostAllocDefault), "cudaHostAlloc")) return rc;
+    r.cap[i] = want;
+  }
+  std::memcpy(r.host[i], src, bytes);
+  if (int rc = check(cudaMallocAsync(d_table, bytes, st), "cudaMallocAsync")) return rc;
+  if (int rc = check(cudaMemcpyAsync(*d_table, r.host[i], bytes, cudaMemcpyHostToDevice, st), "job table H2D")) {
+    cudaFreeAsync(*d_table, st);
+    return rc;
+  }
+  r.used[i] = true;
+  return check(cudaEventRecord(r.ev[i], st), "cudaEventRecord");
+}
+
 struct RowsOpts { int bits, symmetric; };
 
 // Runs every job: stream-class jobs are grouped into <= kMaxInlineJobs batches per
@@ -73,13 +123,45 @@ struct RowsOpts { int bits, symmetric; };
 int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who,
              const aeqb::PeerMirror* peers = nullptr) {
   const int sms = sm_count();
+  bool done_class[5] = {false, false, false, false, false};
   if (peers && peers->n > 0) {  // only the tile-stream kernels mirror their scales
     for (int64_t i = 0; i < n; ++i)
       if (jobs[i].rows > 0 && jobs[i].cols > 0 && aeqb::rows_job_class(jobs[i], o.bits) == 0)
         return fail("%s: tensor %lld ([%lld, %d]) does not take the tile-stream kernel; gather its "
                     "scales with a collective", who, (long long)i, (long long)jobs[i].rows, jobs[i].cols);
   }
+  for (int klass = 1; klass <= 4 && use_job_tables(); ++klass) {  // one launch per class when it is big
+    std::vector<aeqb::RowsJob> tab;
+    long long n_tiles = 0;
+    bool rich = false;
+    for (int64_t i = 0; i < n; ++i) {
+      aeqb::RowsJob j = jobs[i];
+      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != klass) continue;
+      j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
+      j.cpr_magic = static_cast<unsigned>(((1u << 20) + (j.cols / 128) - 1) / (j.cols / 128));
+      j.tile0 = n_tiles;
+      j.tile_end = j.tile0 + (j.rows + j.rows_per_tile - 1) / j.rows_per_tile;
+      n_tiles = j.tile_end;
+      rich |= j.mse_k != 0.0f || j.clip != nullptr || j.given_scale != nullptr;
+      tab.push_back(j);
+    }
+    if (tab.size() <= static_cast<size_t>(aeqb::kMaxInlineJobs)) continue;  // the inline path below takes it
+    void* d_table = nullptr;
+    if (int rc = upload_table(tab.data(), tab.size() * sizeof(aeqb::RowsJob), st, &d_table)) return rc;
+    aeqb::RowsBatch b{};
+    b.bits = o.bits; b.symmetric = o.symmetric;
+    if (peers) b.peers = *peers;
+    b.table = static_cast<const aeqb::RowsJob*>(d_table);
+    b.rich = rich ? 1 : 0;
+    b.n_jobs = static_cast<int>(tab.size());
+    b.n_tiles = n_tiles;
+    const int rc = check(aeqb::launch_requant_rows_stream(b, klass, sms, st), who);
+    cudaFreeAsync(d_table, st);
+    if (rc) return rc;
+    done_class[klass] = true;
+  }
   for (int klass = 1; klass <= 4; ++klass) {
+    if (done_class[klass]) continue;
     aeqb::RowsBatch b{};
     b.bits = o.bits; b.symmetric = o.symmetric;
     if (peers) b.peers = *peers;
@@ -130,6 +212,33 @@ int run_blocks(const aeqb::BlocksJob* jobs, int64_t n, int block, int bits, cuda
     }
   }
   bool bq = false, bp = false;
+  // One launch for a model of more than kMaxInlineJobs streamable tensors with one output set.
+  if (use_job_tables()) {
+    std::vector<aeqb::BlocksJob> tab;
+    long long n_tiles = 0;
+    bool uniform = true, tq = false, tp = false;
+    for (int64_t i = 0; i < n && uniform; ++i) {
+      aeqb::BlocksJob j = jobs[i];
+      if (j.n <= 0) continue;
+      const bool jq = j.q != nullptr, jp = j.packed != nullptr;
+      if (!aeqb::blocks_job_streamable(j) || (!tab.empty() && (jq != tq || jp != tp))) { uniform = false; break; }
+      tq = jq; tp = jp;
+      j.tile0 = n_tiles;
+      j.tile_end = j.tile0 + aeqb::blocks_job_tiles(j.n);
+      n_tiles = j.tile_end;
+      tab.push_back(j);
+    }
+    if (uniform && tab.size() > static_cast<size_t>(aeqb::kMaxInlineJobs)) {
+      void* d_table = nullptr;
+      if (int rc = upload_table(tab.data(), tab.size() * sizeof(aeqb::BlocksJob), st, &d_table)) return rc;
+      b.table = static_cast<const aeqb::BlocksJob*>(d_table);
+      b.n_jobs = static_cast<int>(tab.size());
+      b.n_tiles = n_tiles;
+      const int rc = check(aeqb::launch_requant_blocks_stream(b, tq, tp, sms, st), who);
+      cudaFreeAsync(d_table, st);
+      return rc;
+    }
+  }
   auto flush = [&]() -> int {
     if (b.n_jobs == 0) return 0;
     int rc = check(aeqb::launch_requant_blocks_stream(b, bq, bp, sms, st), who);
@@ -322,7 +431,7 @@ int aeqb_requant_blocks_batch_mirror_f32(const aeqb_blocks_job* jobs, int64_t n_
                     "aeqb_requant_blocks_batch_mirror_f32", &pm);
 }
 
-int aeqb_ema_sequence_f32(const float* pairs, int64_t n, float smoothing, float* out2, void* stream) {
+int aeqb_ema_sequence_f32(const float* pairs, int64_t n, double smoothing, float* out2, void* stream) {
   if (n < 0) return fail("negative batch count");
   if (!out2 || (n > 0 && !pairs)) return fail("pairs / out2 are NULL");
   return check(aeqb::launch_ema_sequence(pairs, n, smoothing, out2, static_cast<cudaStream_t>(stream)),

@@ -58,6 +58,11 @@ struct RowsBatch {
   int symmetric;
   long long n_tiles;
   PeerMirror peers;
+  // A model with more than kMaxInlineJobs tensors travels as ONE launch too: `table` then points
+  // at n_jobs entries in device memory (uploaded by the C ABI from a pinned ring, stream-ordered)
+  // and `jobs` is unused.  `rich`: what the launcher would have derived from the inline jobs.
+  const RowsJob* table;
+  int rich;
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
 int rows_job_class(const RowsJob& j, int bits);
@@ -86,6 +91,7 @@ struct BlocksBatch {
   int bits;
   long long n_tiles;
   PeerMirror peers;  // n > 0: the fp16 scales are also stored into the peers' gathered buffers
+  const BlocksJob* table;  // device job table for more than kMaxInlineJobs tensors (see RowsBatch)
 };
 long long blocks_job_tiles(long long n);
 bool blocks_job_streamable(const BlocksJob& j);
@@ -117,7 +123,7 @@ cudaError_t launch_block_minmax(const float* x, long long n, int block, float* m
                                 cudaStream_t st);
 
 // qsv_utils.moving_average_update folded over n (min, max) pairs in batch order (reduce.cu).
-cudaError_t launch_ema_sequence(const float* pairs, long long n, float smoothing, float* out2,
+cudaError_t launch_ema_sequence(const float* pairs, long long n, double smoothing, float* out2,
                                 cudaStream_t st);
 cudaError_t launch_hist(const float* x, long long n, float lb, float bw, int nbins, int finite_only,
                         long long* counts, int sm_count, cudaStream_t st);

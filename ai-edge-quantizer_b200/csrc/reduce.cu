@@ -481,10 +481,11 @@ __global__ void ema_sequence_kernel(const float* __restrict__ pairs, long long n
   out2[1] = mx;
 }
 
-cudaError_t launch_ema_sequence(const float* pairs, long long n, float smoothing, float* out2,
+cudaError_t launch_ema_sequence(const float* pairs, long long n, double smoothing, float* out2,
                                 cudaStream_t st) {
-  const float s = smoothing;
-  const float c = static_cast<float>(1.0 - static_cast<double>(smoothing));
+  // the Python floats 0.95 and (1.0 - 0.95) are rounded to fp32 separately, from float64
+  const float s = static_cast<float>(smoothing);
+  const float c = static_cast<float>(1.0 - smoothing);
   ema_sequence_kernel<<<1, 32, 0, st>>>(pairs, n, s, c, out2);
   return count_launch();
 }

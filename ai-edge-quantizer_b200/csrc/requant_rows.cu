@@ -210,12 +210,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
   if (warp == NW) {  // ---------------- producer
     if (lane == 0) {
       int j = 0;
-      RowsJob job = b.jobs[0];
+      const RowsJob* jobs = b.table != nullptr ? b.table : b.jobs;  // device table or kernel parameters
+      RowsJob job = jobs[0];
       int s = 0;
       uint32_t round = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        while (tile >= job.tile_end) job = b.jobs[++j];
+        while (tile >= job.tile_end) job = jobs[++j];
         const long long row0 = (tile - job.tile0) * job.rows_per_tile;
         const long long nrows = min(static_cast<long long>(job.rows_per_tile), job.rows - row0);
         desc[s].job = job;
@@ -567,8 +568,8 @@ cudaError_t launch_stream_as(const RowsBatch& b, int sm_count, int ctas_per_sm, 
 // constants or caller-supplied scales takes the rich one.
 template <int STAGE_BYTES, int NW, int SLOTS, int STAGES>
 cudaError_t launch_stream(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
-  bool rich = false;
-  for (int i = 0; i < b.n_jobs; ++i)
+  bool rich = b.table != nullptr && b.rich != 0;
+  for (int i = 0; b.table == nullptr && i < b.n_jobs; ++i)
     rich |= b.jobs[i].mse_k != 0.0f || b.jobs[i].clip != nullptr || b.jobs[i].given_scale != nullptr;
   return rich ? launch_stream_as<STAGE_BYTES, NW, SLOTS, STAGES, true>(b, sm_count, ctas_per_sm, st)
               : launch_stream_as<STAGE_BYTES, NW, SLOTS, STAGES, false>(b, sm_count, ctas_per_sm, st);

@@ -202,9 +202,10 @@ AEQB_API int aeqb_minmax_tensor_f32(const float* x, int64_t n, float lo, float h
 
 /* out2 = qsv_utils.moving_average_update (utils/qsv_utils.py:43-68) folded over n per-batch
  * (min, max) pairs in batch order: the first pair verbatim (calibrator.py:415-416), then
- * smoothing * old + (1 - smoothing) * new in fp32 with NumPy's weak-scalar rounding.  pairs:
+ * smoothing * old + (1 - smoothing) * new in fp32 with NumPy's weak-scalar rounding (the two
+ * float64 coefficients are rounded to fp32 separately, hence `double smoothing`).  pairs:
  * DEVICE [n, 2] (e.g. the all-gathered output of aeqb_minmax_tensors_f32), out2: DEVICE [2]. */
-AEQB_API int aeqb_ema_sequence_f32(const float* pairs, int64_t n, float smoothing, float* out2,
+AEQB_API int aeqb_ema_sequence_f32(const float* pairs, int64_t n, double smoothing, float* out2,
                                    void* stream);
 
 /* counts[clip(int32(floor((x - lower_bound) / bin_width)), 0, nbins - 1)] += 1 for every element

@@ -199,3 +199,55 @@ def test_obs_loop_at_layer_size_vs_f64_replay(cuda, rows, k):
   l, l_ref, l_rtn = loss(q), loss(q_ref), loss(q_rtn)
   assert abs(l - l_ref) <= 1e-3 * l_ref, (l, l_ref)
   assert l < 0.97 * l_rtn, (l, l_rtn)
+
+
+def test_more_than_64_tensors_travel_as_one_launch(cuda, monkeypatch):
+  """A model's weight set above the 64 inline kernel-parameter jobs goes out as ONE persistent
+  launch whose job table sits in device memory (uploaded stream-ordered from a pinned ring):
+  every tensor bit-exact, rows and blocks kernels, with and without mirrored scales; the
+  chained-launch path (AEQB_NO_JOB_TABLE) is covered by the 72-job test in test_gpu_requant."""
+  import ctypes
+  import types
+  import torch
+  from aeq_b200 import _lib, device
+  lib = _lib.load()
+  shapes = [(40 + (i % 5), 4096) for i in range(130)]
+  ws = [O.synthetic_weight(r, c, index=500 + i) for i, (r, c) in enumerate(shapes)]
+  xs = [torch.from_numpy(w).to(cuda) for w in ws]
+  before = lib.aeqb_launch_count()
+  outs = device.requant_rows_batch(xs, 8, True)
+  assert lib.aeqb_launch_count() - before == 1
+  for w, o in zip(ws, outs):
+    ref = O.minmax_requant(w, 8, True)
+    np.testing.assert_array_equal(o.q.cpu().numpy(), ref["q"])
+    np.testing.assert_array_equal(o.scale.cpu().numpy(), ref["scale"])
+  # the same call again reuses the cached host-side job list (steady-state callers) and the ring
+  for _ in range(12):
+    outs2 = device.requant_rows_batch(xs, 8, True, outs=outs)
+  np.testing.assert_array_equal(outs2[129].q.cpu().numpy(), O.minmax_requant(ws[129], 8, True)["q"])
+  # mirrored scales through the table path
+  slots = sum(r for r, _ in shapes)
+  buf = torch.full((2, slots), -1.0, dtype=torch.float32, device=cuda)
+  deltas = (ctypes.c_int64 * 1)(buf[1].data_ptr() - buf[0].data_ptr())
+  mirror = types.SimpleNamespace(deltas_ptr=ctypes.cast(deltas, ctypes.c_void_p), n_peers=1)
+  mo, off = [], 0
+  for r, c in shapes:
+    mo.append(device.Requantized(torch.empty((r, c), dtype=torch.int8, device=cuda), None,
+                                 buf[0, off:off + r].view(r, 1), torch.empty((r, 1), dtype=torch.int32, device=cuda)))
+    off += r
+  before = lib.aeqb_launch_count()
+  device.requant_rows_batch(xs, 8, True, outs=mo, mirror=mirror)
+  assert lib.aeqb_launch_count() - before == 1
+  want = np.concatenate([O.minmax_requant(w, 8, True)["scale"].reshape(-1) for w in ws])
+  got = buf.cpu().numpy()
+  np.testing.assert_array_equal(got[0], want)
+  np.testing.assert_array_equal(got[1], want)
+  # blocks kernel
+  before = lib.aeqb_launch_count()
+  bo = device.requant_blocks_batch(xs, 32, 4, want_q=False, want_packed=True, want_scale=True)
+  assert lib.aeqb_launch_count() - before == 1
+  for w, o in zip(ws[::7], bo[::7]):
+    ref = O.minmax_requant(w, 4, True, block=32)
+    np.testing.assert_array_equal(o.packed.cpu().numpy(), O.pack_bits(4, ref["q"]))
+    np.testing.assert_array_equal(o.scale.cpu().numpy(), ref["scale"])
+    np.testing.assert_array_equal(o.scale_f16.cpu().numpy(), O.blockwise_scale_fp16(ref["scale"]))
