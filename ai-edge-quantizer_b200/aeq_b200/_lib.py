@@ -66,7 +66,7 @@ SIGNATURES = {
     "aeqb_xtx_f32": (_I, [_P, _L, _L, _D, _P, _P, _P]),
     "aeqb_hessian_inverse_workspace_bytes": (_c.c_size_t, [_L]),
     "aeqb_hessian_inverse_f64": (_I, [_P, _L, _D, _I, _P, _P, _P, _P]),
-    "aeqb_gptq_workspace_bytes": (_c.c_size_t, [_L]),
+    "aeqb_gptq_workspace_bytes": (_c.c_size_t, [_L, _L]),
     "aeqb_gptq_quantize_f32": (_I, [_P, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
     "aeqb_hessian_merge_f64": (_I, [_P, _D, _P, _D, _P, _L, _P]),
     "aeqb_scale_zp_from_minmax": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),

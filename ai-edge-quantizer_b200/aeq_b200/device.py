@@ -525,7 +525,7 @@ def gptq_quantize(w: torch.Tensor, hinv: torch.Tensor, scale: torch.Tensor,
       raise ValueError("zero_point must have the shape of scale")
   work = w.clone()
   q = torch.empty((rows, k), dtype=torch.int8, device=w.device)
-  ws = torch.empty(_lib.load().aeqb_gptq_workspace_bytes(rows), dtype=torch.uint8, device=w.device)
+  ws = torch.empty(_lib.load().aeqb_gptq_workspace_bytes(rows, k), dtype=torch.uint8, device=w.device)
   _lib.call("aeqb_gptq_quantize_f32", _ptr(work), rows, k, _ptr(hinv), _ptr(scale), _ptr(zp), cols,
             block, bits, int(symmetric), 64, _ptr(q), _ptr(ws), _stream())
   return q

@@ -581,7 +581,9 @@ int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp, int keep_d
                "aeqb_hessian_inverse_f64");
 }
 
-size_t aeqb_gptq_workspace_bytes(int64_t rows) { return rows > 0 ? aeqb::gptq_workspace_bytes(rows) : 0; }
+size_t aeqb_gptq_workspace_bytes(int64_t rows, int64_t k) {
+  return (rows > 0 && k > 0) ? aeqb::gptq_workspace_bytes(rows, k) : 0;
+}
 
 int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
                            const float* scale, const int32_t* zp, int64_t scale_cols, int block,
@@ -598,7 +600,8 @@ int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* 
   if (rows * k > 0 && (!w_work || !hinv || !scale || !q || !ws)) return fail("w_work / hinv / scale / q / ws are NULL");
   return check(aeqb::launch_gptq_quantize(w_work, rows, k, hinv, scale, zp,
                                           static_cast<int>(scale_cols), block, bits,
-                                          symmetric ? 1 : 0, q, ws, static_cast<cudaStream_t>(stream)),
+                                          symmetric ? 1 : 0, q, ws, sm_count(),
+                                          static_cast<cudaStream_t>(stream)),
                "aeqb_gptq_quantize_f32");
 }
 

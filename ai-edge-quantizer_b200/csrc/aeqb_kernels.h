@@ -163,10 +163,22 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
                                    cudaStream_t st);
 cudaError_t launch_weighted_mean_f64(const double* a, double wa, const double* b, double wb,
                                      double* out, long long n, int sm_count, cudaStream_t st);
-size_t gptq_workspace_bytes(long long R);
+size_t gptq_workspace_bytes(long long R, long long K);
 cudaError_t launch_gptq_quantize(float* w_work, long long R, long long K, const float* hinv,
                                  const float* scale, const int32_t* zp, int row_stride, int qblock,
-                                 int bits, int symmetric, int8_t* q, void* ws, cudaStream_t st);
+                                 int bits, int symmetric, int8_t* q, void* ws, int sm_count,
+                                 cudaStream_t st);
+// Left-looking tensor-core update (gptq_update_tc.cu).
+struct alignas(64) GptqTcMapsOpaque { unsigned char bytes[512]; };  // four CUtensorMap
+bool gptq_update_tc_eligible(long long R, long long K);
+int gptq_update_tc_max_splits();
+int gptq_update_tc_splits(long long R, int kb_total, int sm_count);
+cudaError_t launch_split_planes(const float* x, long long n, float* hi, float* lo, int sm_count,
+                                cudaStream_t st);
+cudaError_t gptq_update_tc_prepare(GptqTcMapsOpaque* out, const float* err_hi, const float* err_lo,
+                                   const float* h_hi, const float* h_lo, long long R, long long K);
+cudaError_t launch_gptq_update_tc(const GptqTcMapsOpaque* maps, float* part, long long R, int c0, int L,
+                                  int n_splits, cudaStream_t st);
 
 // Unfused element-wise pieces (elementwise.cu).
 cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,

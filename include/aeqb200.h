@@ -286,8 +286,12 @@ AEQB_API int aeqb_hessian_inverse_f64(double* hessian, int64_t k, double damp,
  *   scale / zp: scale_cols entries per row: 1 (per channel), k / block (blockwise,
  *   gptq.py:177-189) or 0 (one entry for the whole tensor).  zp may be NULL (zeros).
  *   blocksize: 64 (the reference's only value).  q: [rows, k] int8.
- *   ws: aeqb_gptq_workspace_bytes(rows) bytes (the current block's error matrix). */
-AEQB_API size_t aeqb_gptq_workspace_bytes(int64_t rows);
+ *   ws: aeqb_gptq_workspace_bytes(rows, k) bytes.  Large layers (k a multiple of 64, k >= 1024)
+ *   take the LEFT-looking schedule: before block b, W[:, b] -= Err[:, :64b] @ Hinv[:64b, b] as one
+ *   3xTF32 tcgen05 product per block (same numbers as gptq.py:208-214 regrouped; the error lives
+ *   as two TF32 planes in ws), and w_work is then only read.  Other shapes keep the reference's
+ *   right-looking order with an fp32 SIMT update of w_work. */
+AEQB_API size_t aeqb_gptq_workspace_bytes(int64_t rows, int64_t k);
 AEQB_API int aeqb_gptq_quantize_f32(float* w_work, int64_t rows, int64_t k, const float* hinv,
                                     const float* scale, const int32_t* zp, int64_t scale_cols,
                                     int block, int bits, int symmetric, int blocksize, int8_t* q,

@@ -408,3 +408,66 @@ def test_hadamard_gptq_matches_composed_oracle(cuda, rows, k, max_size):
   # without a Hessian the weight keeps GPTQ's behaviour: parameters only
   r0 = hadamard_gptq.get_tensor_quant_params(_op_info(w, cfg), cfg, w, None)
   assert r0.quantized_data is None
+
+
+@pytest.mark.parametrize("rows,k,bits,sym,gk", [(256, 1024, 4, True, 0), (100, 1152, 4, False, 0),
+                                                (160, 1024, 8, True, 32), (33, 2048, 4, True, 0)])
+def test_left_looking_tensor_core_path_vs_oracle(cuda, rows, k, bits, sym, gk):
+  """K >= 1024 (a multiple of 64) takes the left-looking schedule: lane-per-row column kernel +
+  one 3xTF32 tcgen05 product per block over everything quantised so far.  Same H^-1 on both sides:
+  the first block has no inter-block term (bit-exact), the rest differs from the reference's
+  right-looking loop only by where the update's dot products are rounded."""
+  import torch
+  from aeq_b200 import _lib, device
+  w = O.synthetic_weight(rows, k, rows + k)
+  x = O.synthetic_activation((4, 2 * k, k), k + 1)
+  x = x + 0.5 * np.roll(x, 1, axis=-1)
+  hinv = np.ascontiguousarray(O.gptq_hessian_inverse(O.gptq_hessian(x)))
+  mn, mx = O.weight_minmax(w, max(gk, 0), True)
+  zp, scale = O.scale_zp(mn, mx, bits, sym, gk > 0)
+  with np.errstate(all="ignore"):
+    want = O.gptq_quantize(w, scale, zp, hinv, bits, sym, max(gk, 0))
+  before = _lib.load().aeqb_launch_count()
+  got = device.gptq_quantize(torch.from_numpy(w).to(cuda), torch.from_numpy(hinv).to(cuda),
+                             torch.from_numpy(scale.reshape(-1)).to(cuda),
+                             torch.from_numpy(zp.astype(np.int32).reshape(-1)).to(cuda),
+                             max(gk, 0), bits, sym).cpu().numpy()
+  nblocks = k // 64
+  assert _lib.load().aeqb_launch_count() - before == 1 + nblocks + (nblocks - 1), "not on the left-looking path"
+  np.testing.assert_array_equal(got[:, :64], want[:, :64])
+  d = np.abs(got.astype(int) - want.astype(int))
+  assert (d > 0).mean() <= 5e-3 and d.max() <= 2, ((d > 0).mean(), d.max())
+
+  def loss(qq):
+    s = scale if gk == 0 else np.repeat(scale, gk, axis=1)
+    z = zp if gk == 0 else np.repeat(zp, gk, axis=1)
+    e = (w - (qq.astype(np.float32) - z) * s).astype(np.float64)
+    h = np.linalg.inv(hinv.astype(np.float64))
+    return float(np.einsum("ri,ij,rj->", e, h, e))
+
+  assert abs(loss(got) - loss(want)) <= 1e-3 * loss(want)
+
+
+@pytest.mark.parametrize("rows,k", [(40, 200), (70, 512)])
+def test_lane_per_row_column_kernel_equals_the_row_per_warp_one(cuda, monkeypatch, rows, k):
+  """Shapes below the tensor-core threshold keep the reference's right-looking order; the new
+  lane-per-row column kernel and the round-1 row-per-warp kernel (AEQB_GPTQ_OLD_COLS=1, read once
+  per process, so compared against the oracle instead) give the reference's integers given the
+  same H^-1: single-block shapes bit-exact, multi-block within the update's rounding order."""
+  import torch
+  from aeq_b200 import device
+  w = O.synthetic_weight(rows, k, 7)
+  w[1, :] = 0.0      # scale 1e-9 / 7: outside the exact-divide window -> IEEE redo of the warp
+  w[2, :] = 1e30
+  x = O.synthetic_activation((2, 2 * k, k), 9)
+  hinv = np.ascontiguousarray(O.gptq_hessian_inverse(O.gptq_hessian(x)))
+  for sym in (True, False):
+    mn, mx = O.weight_minmax(w, 0, True)
+    zp, scale = O.scale_zp(mn, mx, 4, sym, False)
+    with np.errstate(all="ignore"):
+      want = O.gptq_quantize(w, scale, zp, hinv, 4, sym)
+    got = device.gptq_quantize(torch.from_numpy(w).to(cuda), torch.from_numpy(hinv).to(cuda),
+                               torch.from_numpy(scale.reshape(-1)).to(cuda),
+                               torch.from_numpy(zp.astype(np.int32).reshape(-1)).to(cuda), 0, 4, sym).cpu().numpy()
+    np.testing.assert_array_equal(got[:, :64], want[:, :64])
+    assert (got != want).mean() <= 5e-3

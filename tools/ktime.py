@@ -98,7 +98,7 @@ def main():
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     lib.aeqb_hessian_inverse_f64(P(h), C, 0.01, 0, P(hinv), P(hws), P(info), st)
     work = f32(R, C)
-    gws = torch.empty(lib.aeqb_gptq_workspace_bytes(R), dtype=torch.uint8, device=dev)
+    gws = torch.empty(lib.aeqb_gptq_workspace_bytes(R, C), dtype=torch.uint8, device=dev)
     sc = (ws_in[0].abs().amax(dim=1) / 7.0).contiguous()
     cases.append(("xtx 8192 tokens (gptq hessian)", lambda i: lib.aeqb_xtx_f32(
         P(x), 8192, C, 0.25, P(h), P(xws) if xws_n else None, st), 0))
