@@ -147,11 +147,16 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
     }
     if (tab.size() <= static_cast<size_t>(aeqb::kMaxInlineJobs)) continue;  // the inline path below takes it
     void* d_table = nullptr;
-    if (int rc = upload_table(tab.data(), tab.size() * sizeof(aeqb::RowsJob), st, &d_table)) return rc;
+    const size_t ends_bytes = (tab.size() * sizeof(long long) + 127) & ~size_t(127);
+    std::vector<unsigned char> blob(ends_bytes + tab.size() * sizeof(aeqb::RowsJob));
+    for (size_t t = 0; t < tab.size(); ++t) reinterpret_cast<long long*>(blob.data())[t] = tab[t].tile_end;
+    std::memcpy(blob.data() + ends_bytes, tab.data(), tab.size() * sizeof(aeqb::RowsJob));
+    if (int rc = upload_table(blob.data(), blob.size(), st, &d_table)) return rc;
     aeqb::RowsBatch b{};
     b.bits = o.bits; b.symmetric = o.symmetric;
     if (peers) b.peers = *peers;
-    b.table = static_cast<const aeqb::RowsJob*>(d_table);
+    b.table_ends = static_cast<const long long*>(d_table);
+    b.table = reinterpret_cast<const aeqb::RowsJob*>(static_cast<unsigned char*>(d_table) + ends_bytes);
     b.rich = rich ? 1 : 0;
     b.n_jobs = static_cast<int>(tab.size());
     b.n_tiles = n_tiles;
@@ -230,8 +235,13 @@ int run_blocks(const aeqb::BlocksJob* jobs, int64_t n, int block, int bits, cuda
     }
     if (uniform && tab.size() > static_cast<size_t>(aeqb::kMaxInlineJobs)) {
       void* d_table = nullptr;
-      if (int rc = upload_table(tab.data(), tab.size() * sizeof(aeqb::BlocksJob), st, &d_table)) return rc;
-      b.table = static_cast<const aeqb::BlocksJob*>(d_table);
+      const size_t ends_bytes = (tab.size() * sizeof(long long) + 127) & ~size_t(127);
+      std::vector<unsigned char> blob(ends_bytes + tab.size() * sizeof(aeqb::BlocksJob));
+      for (size_t t = 0; t < tab.size(); ++t) reinterpret_cast<long long*>(blob.data())[t] = tab[t].tile_end;
+      std::memcpy(blob.data() + ends_bytes, tab.data(), tab.size() * sizeof(aeqb::BlocksJob));
+      if (int rc = upload_table(blob.data(), blob.size(), st, &d_table)) return rc;
+      b.table_ends = static_cast<const long long*>(d_table);
+      b.table = reinterpret_cast<const aeqb::BlocksJob*>(static_cast<unsigned char*>(d_table) + ends_bytes);
       b.n_jobs = static_cast<int>(tab.size());
       b.n_tiles = n_tiles;
       const int rc = check(aeqb::launch_requant_blocks_stream(b, tq, tp, sms, st), who);

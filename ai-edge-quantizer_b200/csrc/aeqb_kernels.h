@@ -62,6 +62,8 @@ struct RowsBatch {
   // at n_jobs entries in device memory (uploaded by the C ABI from a pinned ring, stream-ordered)
   // and `jobs` is unused.  `rich`: what the launcher would have derived from the inline jobs.
   const RowsJob* table;
+  const long long* table_ends;  // tile_end of every table entry, packed (16 per 128-byte line): the
+                                // producer's walk over hundreds of small tensors reads these, not the jobs
   int rich;
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
@@ -92,6 +94,7 @@ struct BlocksBatch {
   long long n_tiles;
   PeerMirror peers;  // n > 0: the fp16 scales are also stored into the peers' gathered buffers
   const BlocksJob* table;  // device job table for more than kMaxInlineJobs tensors (see RowsBatch)
+  const long long* table_ends;
 };
 long long blocks_job_tiles(long long n);
 bool blocks_job_streamable(const BlocksJob& j);

@@ -267,12 +267,38 @@ __global__ void __launch_bounds__(WarpRowsCfg<NV>::kWarps * 32, WarpRowsCfg<NV>:
       }
     }
 
+    // The first two iterates are known without touching the masks on ordinary weights: the start
+    // guess 1 selects nothing when the row's largest magnitude is below 1 (sum 0, count 0 ->
+    // guess 0), and the guess 0 selects every element that is not a NaN, so that iteration is a
+    // plain packed sum (same accumulators, same order: a * 1.0f + s == a + s, bit-identical) with
+    // the count known in advance.  `row_max` / `has_nan` come from the load.
+    float row_max = 0.0f;
+    bool has_nan = false;
+    if (SKIP) {
+      row_max = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(slot_max)));
+      float mn = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) mn = fminf(mn, fminf(fminf(a[j].x, a[j].y), fminf(a[j].z, a[j].w)));
+      has_nan = __any_sync(0xffffffffu, mn < 0.0f);  // conditioned NaNs are -1
+    }
+
     float g = 1.0f;
     int it = 0;
     for (; it < iters; ++it) {
       float2 s0 = make_float2(0.f, 0.f), s1 = s0, c0 = s0, c1 = s0;
       const unsigned active = SKIP ? __ballot_sync(0xffffffffu, slot_max >= g) : 0xffffffffu;
-      if (g == g) {  // a NaN guess selects nothing
+      const bool nothing = SKIP && g == g && g > row_max;              // no element reaches the guess
+      const bool everything = SKIP && g == 0.0f && !has_nan && FULL;   // every element is selected
+      if (everything) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 2) {
+          s0 = __fadd2_rn(make_float2(a[j].x, a[j].y), s0);
+          s1 = __fadd2_rn(make_float2(a[j].z, a[j].w), s1);
+          s0 = __fadd2_rn(make_float2(a[j + 1].x, a[j + 1].y), s0);
+          s1 = __fadd2_rn(make_float2(a[j + 1].z, a[j + 1].w), s1);
+        }
+        c0 = make_float2(static_cast<float>(4 * NV), 0.0f);  // this lane's 4 * NV elements, all selected
+      } else if (g == g && !nothing) {  // a NaN guess selects nothing
         // Eight masks are formed before the four packed FMAs / adds that consume them: the
         // compare runs on the half-rate ALU pipe with a longer latency than the FMA pipe, and a
         // warp has at most three neighbours on its scheduler to hide that behind.

@@ -103,12 +103,20 @@ __global__ void __launch_bounds__((kNW + 1) * 32, 2)
     if (lane == 0) {
       int j = 0;
       const BlocksJob* jobs = b.table != nullptr ? b.table : b.jobs;  // device table or kernel parameters
+      const long long* ends = b.table_ends;
       BlocksJob job = jobs[0];
       int s = 0;
       uint32_t round = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        while (tile >= job.tile_end) job = jobs[++j];
+        if (ends != nullptr) {
+          if (tile >= job.tile_end) {
+            while (tile >= __ldg(ends + j)) ++j;
+            job = jobs[j];
+          }
+        } else {
+          while (tile >= job.tile_end) job = jobs[++j];
+        }
         const long long e0 = (tile - job.tile0) * kStageFloats;
         const long long ne = min(static_cast<long long>(kStageFloats), job.n - e0);
         desc[s].job = job;

@@ -211,12 +211,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     if (lane == 0) {
       int j = 0;
       const RowsJob* jobs = b.table != nullptr ? b.table : b.jobs;  // device table or kernel parameters
+      const long long* ends = b.table_ends;
       RowsJob job = jobs[0];
       int s = 0;
       uint32_t round = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        while (tile >= job.tile_end) job = jobs[++j];
+        if (ends != nullptr) {  // walk the packed tile ends (L1-resident lines), fetch a job only when it changes
+          if (tile >= job.tile_end) {
+            while (tile >= __ldg(ends + j)) ++j;
+            job = jobs[j];
+          }
+        } else {
+          while (tile >= job.tile_end) job = jobs[++j];
+        }
         const long long row0 = (tile - job.tile0) * job.rows_per_tile;
         const long long nrows = min(static_cast<long long>(job.rows_per_tile), job.rows - row0);
         desc[s].job = job;
