@@ -444,7 +444,13 @@ def _write_subgraph(b: fb.Builder, g: SubGraphT) -> int:
   return b.end_table()
 
 
-EXTERNAL_BUFFER_THRESHOLD = (1 << 31) - (1 << 24)
+# The reference's ModelModifier moves every buffer of 1 KiB or more out of the flatbuffer as soon
+# as those buffers add up to 256 KiB (model_modifier.py:43-75, :202-215): payloads follow the
+# flatbuffer, each 16-byte aligned, and the buffer tables carry `offset` / `size`.  Same rule
+# here; it is also what keeps models above the 2 GB flatbuffer limit writable, and it means a
+# payload is copied once (into the output) instead of twice (builder, then output).
+EXTERNAL_MIN_BUFFER_BYTES = 1024
+EXTERNAL_MIN_TOTAL_BYTES = 256 * 1024
 
 
 def _payload(x: BufferT):
@@ -455,26 +461,56 @@ def _payload(x: BufferT):
   return np.ascontiguousarray(np.asarray(x.data).view(np.uint8) if isinstance(x.data, np.ndarray) else x.data)
 
 
+def _copy_pieces(out: bytearray, pieces) -> None:
+  """out[pos : pos + len(src)] = src for every (pos, src); large models on a few threads (the
+  destination is fresh memory: page faults and the copy both spread over the cores, NumPy drops
+  the GIL while it copies)."""
+  dst = np.frombuffer(out, dtype=np.uint8)
+  jobs = []
+  step = 8 << 20
+  for pos, src in pieces:
+    a = np.frombuffer(src, dtype=np.uint8) if not isinstance(src, np.ndarray) else src.reshape(-1).view(np.uint8)
+    for o in range(0, a.size, step):
+      jobs.append((pos + o, a[o:o + step]))
+  total = sum(a.size for _, a in jobs)
+  if total < (64 << 20):
+    for pos, a in jobs:
+      dst[pos:pos + a.size] = a
+    return
+  from concurrent.futures import ThreadPoolExecutor
+
+  def put(job):
+    dst[job[0]:job[0] + job[1].size] = job[1]
+  with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
+    list(ex.map(put, jobs))
+
+
 def write_model_to_bytes(m: ModelT, external_buffers: Optional[bool] = None):
-  """Serialises the object tree.  Buffer payloads are 16-byte aligned like the schema's
-  `force_align: 16`.  A flatbuffer addresses 2 GB, so when the payloads reach that size (or
-  `external_buffers=True`) they are written AFTER the flatbuffer, each 16-byte aligned, and the
-  buffer tables carry `offset` / `size` instead of `data` — the layout of the reference's
-  `ModelModifier._serialize_model` (model_modifier.py:290-377), which is also what
-  `read_model_from_bytes` resolves back into views."""
+  """Serialises the object tree; returns bytes (or a bytearray when buffers are external).
+
+  external_buffers: None = the reference's rule (see above), True / False = force.  Inline
+  payloads are 16-byte aligned like the schema's `force_align: 16`; external ones follow the
+  flatbuffer, 16-byte aligned, and `read_model_from_bytes` resolves them back into views."""
   payloads = [_payload(x) for x in m.buffers]
-  total = sum(0 if p is None else len(p) for p in payloads)
+  big = sum(len(p) for p in payloads if p is not None and len(p) >= EXTERNAL_MIN_BUFFER_BYTES)
+  forced = external_buffers is True
   if external_buffers is None:
-    external_buffers = total >= EXTERNAL_BUFFER_THRESHOLD
-  b = fb.Builder(max(1 << 16, (0 if external_buffers else int(total * 1.05)) + (1 << 16)))
+    external_buffers = big >= EXTERNAL_MIN_TOTAL_BYTES
+  # automatic: buffers of 1 KiB and more leave the flatbuffer; forced: every non-empty buffer does
+  is_ext = [bool(external_buffers) and p is not None and (forced or len(p) >= EXTERNAL_MIN_BUFFER_BYTES)
+            for p in payloads]
+  inline_total = sum(len(p) for p, e in zip(payloads, is_ext) if p is not None and not e)
+  if inline_total >= (1 << 31) - (1 << 24):
+    raise ValueError("more than 2 GB of buffers would stay inside the flatbuffer")
+  b = fb.Builder(max(1 << 16, int(inline_total * 1.05) + (1 << 16)))
   buffers = []
-  for x, payload in zip(m.buffers, payloads):
+  for x, payload, ext in zip(m.buffers, payloads, is_ext):
     data = 0
-    if payload is not None and not external_buffers:
+    if payload is not None and not ext:
       data = b.create_byte_vector(payload, align=16)
     b.start_table()
     b.add_offset(0, data)
-    if payload is not None and external_buffers:
+    if ext:
       b.add_scalar(1, "ulong", 1)  # placeholders: non-default, so the fields exist and can be
       b.add_scalar(2, "ulong", 1)  # patched once the payload positions are known
     else:
@@ -533,21 +569,23 @@ def write_model_to_bytes(m: ModelT, external_buffers: Optional[bool] = None):
   b.add_offset(6, meta_v)
   b.add_offset(7, sigs_v)
   head = b.finish(b.end_table(), FILE_IDENTIFIER)
-  if not external_buffers:
+  if not any(is_ext):
     return head
   r16 = lambda n: (n + 15) & ~15
-  out = bytearray(r16(len(head)) + sum(r16(len(p)) for p in payloads if p is not None))
+  out = bytearray(r16(len(head)) + sum(r16(len(p)) for p, e in zip(payloads, is_ext) if e))
   out[:len(head)] = head
   tables = fb.Table.root(head).table_vector(4)
   pos = r16(len(head))
-  for t, payload in zip(tables, payloads):
-    if payload is None:
+  pieces = []
+  for t, payload, ext in zip(tables, payloads, is_ext):
+    if not ext:
       continue
     n = len(payload)
     struct.pack_into("<Q", out, t._field(1), pos)  # pylint: disable=protected-access
     struct.pack_into("<Q", out, t._field(2), n)    # pylint: disable=protected-access
-    out[pos:pos + n] = memoryview(payload).cast("B")
+    pieces.append((pos, payload))
     pos = r16(pos + n)
+  _copy_pieces(out, pieces)
   return out
 
 
