@@ -16,6 +16,7 @@ from .algorithms.nonlinear_quantize import float_casting
 from .algorithms.uniform_quantize import dequantized_weight_recovery
 from .algorithms.uniform_quantize import gptq
 from .algorithms.uniform_quantize import hadamard_rotation
+from .algorithms.uniform_quantize import histogram_calibration
 from .algorithms.uniform_quantize import mse
 from .algorithms.uniform_quantize import naive_min_max_quantize
 from .algorithms.uniform_quantize import octav
@@ -104,6 +105,13 @@ register_weight_algorithm(AlgorithmName.OCTAV, octav.get_tensor_quant_params,
                           naive_min_max_quantize.min_max_calibrate)
 register_weight_algorithm(AlgorithmName.MSE, mse.get_tensor_quant_params,
                           naive_min_max_quantize.min_max_calibrate)
+# Histogram calibration: the reference ships utils/histogram_utils.py but
+# binds it to no algorithm, so the key is ours (a plain string, not an `AlgorithmName` member:
+# that enum stays equal to the reference's).  Weights quantise exactly like min-max.
+register_weight_algorithm(histogram_calibration.ALGORITHM_KEY,
+                          histogram_calibration.get_tensor_quant_params,
+                          histogram_calibration.histogram_calibrate,
+                          update_qsv_func=histogram_calibration.histogram_update)
 # Weight-only rotation; the reference's own FC / EMBEDDING materialisers add the
 # activation-side INSERT_HADAMARD_ROTATION (hadamard_rotation.py:206-500) and are
 # reached through plugin.install.

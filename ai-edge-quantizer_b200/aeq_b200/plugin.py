@@ -213,6 +213,32 @@ def install(reference_algorithm_manager, algorithms=None, calibration: bool = Tr
   return bound
 
 
+def install_histogram(reference_algorithm_manager, ops=None) -> str:
+  """Registers `histogram_min_max_uniform_quantize` in the REFERENCE's registry: for every op the
+  reference's min-max algorithm covers, its own materialiser partially applied to our
+  histogram-aware `get_tensor_quant_params`, `histogram_calibrate` as the calibration function
+  and `histogram_update` as the QSV merge (register_quantized_op, algorithm_manager_api.py:191-227).
+  A recipe then names the key as its algorithm; returns the key."""
+  from .algorithms.uniform_quantize import histogram_calibration as hc
+  am = reference_algorithm_manager
+  adapted = _adapt(hc.get_tensor_quant_params, am.qtyping)
+  for op_name, materialize_func in am.MIN_MAX_OP_NAME_MATERIALIZE_FUNC_DICT.items():
+    if ops is not None and op_name not in ops:
+      continue
+    inner = materialize_func.func if isinstance(materialize_func, functools.partial) else materialize_func
+    am.register_quantized_op(
+        hc.ALGORITHM_KEY, op_name, am.naive_min_max_quantize.init_qsvs,
+        calibration_func=hc.histogram_calibrate,
+        materialize_func=functools.partial(inner, adapted),
+        update_qsv_func=hc.histogram_update)
+  am.register_op_quant_config_validation_func(
+      hc.ALGORITHM_KEY, am.common_quantize.check_op_quantization_config)
+  policy = getattr(am, "default_policy", None)
+  if policy is not None and hasattr(am, "register_config_check_policy_func"):
+    am.register_config_check_policy_func(hc.ALGORITHM_KEY, policy.DEFAULT_CONFIG_CHECK_POLICY)
+  return hc.ALGORITHM_KEY
+
+
 def prefetch(params_generator, model_recipe_manager) -> dict:
   """Quantises all min-max weights of the reference ParamsGenerator's model in a few batched
   launches and fills its `(buffer, config)` cache; call it right before

@@ -150,3 +150,88 @@ def requantize_sharded(weights: Sequence[np.ndarray], compute: Callable[[list[np
   scales = allgather_vectors(local, [scale_length(w) for w in weights], owner, group,
                              dtype=torch.float32, device=device or torch.device("cpu"))
   return owner, dict(zip(mine, results)), scales
+
+
+# ------------------------------------------------------------------ row-split units (SURVEY.md §8e "Partitioning")
+def split_units(shapes: Sequence[Sequence[int]], world: int, itemsize: int = 4,
+                threshold: float = 0.5, row_align: int = 1) -> list[tuple[int, int, int]]:
+  """Units of work [(tensor index, first row, end row)] in tensor order.
+
+  A tensor is one unit unless its bytes exceed `threshold` x (total bytes / world) — the balance
+  threshold: one such tensor alone would tip a rank over its fair share.  It is then cut BY ROWS
+  into the fewest near-equal pieces that fit under the threshold.  Rows are the separable axis of
+  the path: a per-channel row and every 32..256-block lie inside one row of the [rows, cols] view
+  (common_quantize.py:1337-1344, uqt:246-262), so a piece is requantised exactly as the whole
+  tensor would be.  Only TENSORWISE granularity couples the pieces, through one (min, max) pair:
+  `allreduce_minmax`.  `row_align` keeps piece boundaries on a multiple of rows (e.g. 2 when INT4
+  rows of odd length are packed across the row boundary).  Deterministic: every rank computes the
+  same list without communicating.
+  """
+  if world < 1:
+    raise ValueError("world size must be >= 1")
+  sizes = [int(np.prod(s)) * itemsize for s in shapes]
+  fair = sum(sizes) / world if sizes else 0.0
+  limit = threshold * fair
+  units = []
+  for i, (shape, nbytes) in enumerate(zip(shapes, sizes)):
+    rows = int(shape[0]) if len(shape) else 1
+    pieces = 1
+    if world > 1 and limit > 0 and nbytes > limit:
+      pieces = min(int(-(-nbytes // limit)), max(rows // max(row_align, 1), 1))
+    if pieces <= 1:
+      units.append((i, 0, rows))
+      continue
+    per = -(-rows // pieces)
+    per = -(-per // row_align) * row_align
+    r0 = 0
+    while r0 < rows:
+      units.append((i, r0, min(r0 + per, rows)))
+      r0 += per
+  return units
+
+
+def unit_sizes(units: Sequence[tuple[int, int, int]], shapes: Sequence[Sequence[int]],
+               itemsize: int = 4) -> list[int]:
+  return [(r1 - r0) * int(np.prod(shapes[i][1:])) * itemsize for i, r0, r1 in units]
+
+
+def allreduce_minmax(local: torch.Tensor, group=None) -> torch.Tensor:
+  """Per-tensor (min, max) pairs combined over the ranks that hold rows of the tensor: ONE
+  all-reduce(MAX) of [-min, max] (2 floats per split tensor).  A rank holding no row of a tensor
+  passes (+inf, -inf).  NaNs follow the local reduction's rule before they get here."""
+  rank, world = _world(group)
+  if world == 1:
+    return local
+  packed = torch.stack([-local[:, 0], local[:, 1]], dim=1).contiguous()
+  dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=group)
+  return torch.stack([-packed[:, 0], packed[:, 1]], dim=1)
+
+
+def requantize_row_sharded(weights: Sequence[np.ndarray], compute: Callable[[list[np.ndarray]], list],
+                           scale_length: Callable[[np.ndarray], int], group=None,
+                           device: Optional[torch.device] = None, threshold: float = 0.5,
+                           row_align: int = 1):
+  """`requantize_sharded` with tensors above the balance threshold cut by rows.
+
+  compute / scale_length see row slices `w[r0:r1]` (views, no copy) of the split tensors.
+  Returns (units, owner of each unit, {unit index: result tuple} for owned units,
+  [scale vector of every TENSOR], pieces concatenated in row order).
+  """
+  rank, world = _world(group)
+  shapes = [w.shape for w in weights]
+  units = split_units(shapes, world, weights[0].dtype.itemsize if len(weights) else 4, threshold, row_align)
+  owner = assign_tensors(unit_sizes(units, shapes, weights[0].dtype.itemsize if len(weights) else 4), world)
+  mine = owned(owner, rank)
+  views = [weights[i][r0:r1] for i, r0, r1 in (units[u] for u in mine)]
+  results = compute(views) if mine else []
+  local = {}
+  for u, res in zip(mine, results):
+    s = torch.from_numpy(np.ascontiguousarray(res[2]).reshape(-1))
+    local[u] = s.to(device) if device is not None else s
+  lengths = [scale_length(weights[i][r0:r1]) for i, r0, r1 in units]
+  per_unit = allgather_vectors(local, lengths, owner, group, dtype=torch.float32,
+                               device=device or torch.device("cpu"))
+  scales: list[list[torch.Tensor]] = [[] for _ in weights]
+  for (i, _, _), v in zip(units, per_unit):
+    scales[i].append(v)
+  return units, owner, dict(zip(mine, results)), [torch.cat(p) if len(p) > 1 else p[0] for p in scales]

@@ -357,3 +357,29 @@ def test_plugin_prefetch_walks_the_model_like_the_reference(monkeypatch):
   assert info.op_name == rq.TFLOperationName.FULLY_CONNECTED and info.subgraph_op_index == 0
   assert graph.buffers is model.buffers and seen["cache"] is pg._tensor_quant_params_cache
   assert isinstance(seen["params"], rq.UniformQuantParams) and seen["data"].shape == (8, 16)
+
+
+def test_histogram_calibration_host_logic():
+  """Percentile range and QSV merge of the histogram calibration algorithm (host side only)."""
+  from aeq_b200.algorithms.uniform_quantize import histogram_calibration as hc
+  assert am.is_algorithm_registered(hc.ALGORITHM_KEY)
+  assert am.get_update_qsv_func(hc.ALGORITHM_KEY, Op.FULLY_CONNECTED) is hc.histogram_update
+  assert hc.ALGORITHM_KEY not in {a.value for a in am.AlgorithmName}  # the enum stays the reference's
+  counts = np.zeros(100, np.int64)
+  counts[10:90] = 10  # 800 values, uniform over bins 10..89
+  ch = {"hist_counts": counts, "lower_bound": -5.0, "bin_width": 0.1, "min": np.array([-4.0]),
+        "max": np.array([4.0])}
+  hist = {"min": -4.0, "max": 4.0, "axis": None, "channels": [ch]}
+  lo, hi = hc.percentile_range(hist, 100.0)
+  assert lo == np.float32(-5.0 + 10 * 0.1) and hi == np.float32(-5.0 + 90 * 0.1)
+  lo, hi = hc.percentile_range(hist, 95.0)  # 20 values trimmed per side = two bins
+  assert lo == np.float32(-5.0 + 12 * 0.1) and hi == np.float32(-5.0 + 88 * 0.1)
+  assert hc.percentile_range({}, 99.0) is None
+  with pytest.raises(ValueError, match="percentile"):
+    hc.set_percentile(40.0)
+  a = {"min": np.array([[-1.0]], np.float32), "max": np.array([[2.0]], np.float32), hc.HISTOGRAM_KEY: hist}
+  b = {"min": np.array([[-3.0]], np.float32), "max": np.array([[4.0]], np.float32), hc.HISTOGRAM_KEY: hist}
+  assert hc.histogram_update({}, a)[hc.HISTOGRAM_KEY]["channels"][0]["hist_counts"].sum() == 800
+  m = hc.histogram_update(a, b)
+  assert m["min"] == np.float32(0.95) * np.float32(-1.0) + np.float32(1 - 0.95) * -3.0 or np.isclose(m["min"], -1.1)
+  assert int(np.sum(m[hc.HISTOGRAM_KEY]["channels"][0]["hist_counts"])) == 1600

@@ -139,3 +139,59 @@ def test_world2_peer_setup_fails_together(tmp_path, fake_success_on):
     assert "allocating the peer-visible buffer failed on at least one rank" in outcome
     if r in fake_success_on:
       assert calls.split(",") == ["aeqb_peer_alloc", "aeqb_peer_free"]
+
+
+def test_split_units_cut_heavy_tensors_by_rows():
+  """One [16384, 2048] among small tensors: whole-tensor LPT cannot balance 2 ranks, row pieces can."""
+  shapes = [(16384, 2048)] + [(256, 2048)] * 6
+  sizes = [r * c * 4 for r, c in shapes]
+  assert sharding.imbalance(sizes, sharding.assign_tensors(sizes, 2), 2) > 1.6
+  units = sharding.split_units(shapes, 2)
+  assert units == sharding.split_units(shapes, 2)
+  us = sharding.unit_sizes(units, shapes)
+  assert sum(us) == sum(sizes)
+  assert sharding.imbalance(us, sharding.assign_tensors(us, 2), 2) < 1.1
+  rows = sorted((r0, r1) for i, r0, r1 in units if i == 0)
+  assert rows[0][0] == 0 and rows[-1][1] == 16384 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+  assert all(u in units for u in [(k, 0, 256) for k in range(1, 7)])
+  assert sharding.split_units(shapes, 1) == [(i, 0, s[0]) for i, s in enumerate(shapes)]
+  assert all((r1 - r0) % 32 == 0 or r1 == 1000 for _, r0, r1 in sharding.split_units([(1000, 64)], 4, row_align=32))
+  with pytest.raises(ValueError):
+    sharding.split_units(shapes, 0)
+
+
+def _split_worker(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    shapes = [(512, 128), (16, 64), (8, 256)]
+    ws = [O.synthetic_weight(r, c, i) for i, (r, c) in enumerate(shapes)]
+    compute = lambda arrs: [(r["q"], None, r["scale"], None) for r in (O.minmax_requant(a, 8, True) for a in arrs)]
+    units, owner, mine, scales = sharding.requantize_row_sharded(ws, compute, lambda w: w.shape[0])
+    held = [units[u] for u in mine]
+    # per-tensor granularity: each rank reduces the rows it holds, one all-reduce of 2 floats joins them
+    mm = torch.tensor([[np.inf, -np.inf]] * len(ws), dtype=torch.float32)
+    for i, r0, r1 in held:
+      mm[i, 0] = min(float(mm[i, 0]), float(ws[i][r0:r1].min()))
+      mm[i, 1] = max(float(mm[i, 1]), float(ws[i][r0:r1].max()))
+    mm = sharding.allreduce_minmax(mm)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), units=np.array(units), owner=np.array(owner),
+             mm=mm.numpy(), held=np.array(held), **{f"s{i}": s.numpy() for i, s in enumerate(scales)})
+  finally:
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_row_split_and_minmax_allreduce(tmp_path):
+  """The heavy tensor is cut by rows over both ranks; every rank ends with the whole scale vector
+  (bit-exact vs the unsplit oracle) and the tensor-wise (min, max) of the split tensor."""
+  port = _free_port()
+  mp.start_processes(_split_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+  got = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+  assert np.array_equal(got[0]["units"], got[1]["units"]) and np.array_equal(got[0]["owner"], got[1]["owner"])
+  assert {tuple(h)[0] for h in got[0]["held"]} & {tuple(h)[0] for h in got[1]["held"]} == {0}  # both hold rows of tensor 0
+  for i, (r, c) in enumerate([(512, 128), (16, 64), (8, 256)]):
+    w = O.synthetic_weight(r, c, i)
+    want = O.minmax_requant(w, 8, True)["scale"].reshape(-1)
+    for g in got:
+      np.testing.assert_array_equal(g[f"s{i}"], want)
+      assert g["mm"][i, 0] == w.min() and g["mm"][i, 1] == w.max()
