@@ -155,12 +155,15 @@ bool xtx_tc_eligible(long long T, long long K);
 size_t xtx_tc_workspace_bytes(long long T, long long K);
 template <typename OutT>
 cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha, OutT* out,
-                          void* ws, int sm_count, const int** flag_out, cudaStream_t st);
+                          void* ws, int sm_count, const int** flag_out, cudaStream_t st, int lower_tri = 0);
 cudaError_t launch_xtx_f64(const float* x, long long T, long long K, double alpha, double* out,
                            void* ws, int sm_count, cudaStream_t st);
 cudaError_t launch_xtx_f32(const float* x, long long T, long long K, double alpha, float* out,
                            void* ws, int sm_count, cudaStream_t st);
 size_t hessian_inverse_workspace_bytes(long long K);
+// chol_dmma.cu: blocked fp64 Cholesky with DMMA rank-128 updates and one-step lookahead
+size_t cholesky_dmma_workspace_bytes();
+cudaError_t launch_cholesky_dmma(double* A, int K, double* linv, int* info, cudaStream_t st, int* launches);
 cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, int mutate_diagonal,
                                    float* hinv, void* ws, int* info_out, int sm_count,
                                    cudaStream_t st);

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256)
 // (10.3 / 84.9 ms): one CTA per SM with single-buffered slabs exposes the global-load latency.
 constexpr int CNB = 128;   // outer block width
 constexpr int kCholTwoLevelMinK = 0;
+constexpr int kCholDmmaMinK = 0;   // default: every size takes chol_dmma.cu
 constexpr int kCholPanel2Smem = CR * (CB + 1) * 8;  // dynamic: the row staging tile
 
 // Panel at columns [j, j + CB), outer block starting at column J <= j (w = j - J pending columns).
@@ -713,7 +714,7 @@ size_t xtx_split_workspace_bytes(long long T, long long K, int sm_count) {
 
 template <typename OutT>
 cudaError_t xtx_impl(const float* x, long long T, long long K, double alpha, OutT* out, void* ws,
-                     size_t ws_bytes, int sm_count, cudaStream_t st) {
+                     size_t ws_bytes, int sm_count, cudaStream_t st, int lower_tri = 0) {
   if (K <= 0) return cudaSuccess;
   const int k = static_cast<int>(K);
   const int nb = (k + XT - 1) / XT;
@@ -723,7 +724,7 @@ cudaError_t xtx_impl(const float* x, long long T, long long K, double alpha, Out
   if (ws && use_tensor_cores(T, K) && ws_bytes >= xtx_tc_workspace_bytes(T, K) &&
       reinterpret_cast<uintptr_t>(ws) % 16 == 0) {
     const int* gate = nullptr;
-    cudaError_t e = launch_xtx_tc<OutT>(x, T, K, alpha, out, ws, sm_count, &gate, st);
+    cudaError_t e = launch_xtx_tc<OutT>(x, T, K, alpha, out, ws, sm_count, &gate, st, lower_tri);
     if (e == cudaSuccess) {
       xtx_tile<OutT><<<dim3(tiles, 1), 256, 0, st>>>(x, T, k, alpha, out, nullptr, T, gate);
       return count_launch();
@@ -772,8 +773,13 @@ static size_t hinv_scratch_bytes(long long K) {
   if (x > a) a = x;
   return (a + 1023) / 1024 * 1024;
 }
+// ... | info (256 B) | pad to 256 | Linv of the current diagonal block (chol_dmma.cu)
+static size_t hinv_linv_offset(long long K) {
+  const size_t o = hinv_scratch_bytes(K) + static_cast<size_t>(K) * K * sizeof(float) + 256;
+  return (o + 255) / 256 * 256;
+}
 size_t hessian_inverse_workspace_bytes(long long K) {
-  return hinv_scratch_bytes(K) + static_cast<size_t>(K) * K * sizeof(float) + 256;
+  return hinv_linv_offset(K) + cholesky_dmma_workspace_bytes();
 }
 
 cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, int mutate_diagonal,
@@ -799,7 +805,12 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   }
   int two_level_min_k = kCholTwoLevelMinK;  // AEQB_CHOL_TWO_LEVEL_MIN_K: A/B runs and tests
   if (const char* e2 = getenv("AEQB_CHOL_TWO_LEVEL_MIN_K")) two_level_min_k = atoi(e2);
-  if (k >= two_level_min_k) {
+  int dmma_min_k = kCholDmmaMinK;  // AEQB_CHOL_DMMA_MIN_K: the DMMA / lookahead factorisation (chol_dmma.cu)
+  if (const char* e3 = getenv("AEQB_CHOL_DMMA_MIN_K")) dmma_min_k = atoi(e3);
+  if (k >= dmma_min_k) {
+    e = launch_cholesky_dmma(A, k, reinterpret_cast<double*>(p + hinv_linv_offset(K)), info, st, &launches);
+    if (e != cudaSuccess) return e;
+  } else if (k >= two_level_min_k) {
     static bool panel2_configured = false;
     if (!panel2_configured) {
       e = cudaFuncSetAttribute(chol_panel2, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholPanel2Smem);
@@ -848,7 +859,7 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
   if (e != cudaSuccess) return e;
   // H^-1 = Y^T Y (einsum "ji,jk->ik"): the same contraction as the Hessian itself.  The split
   // workspace may reuse A + L32, which are dead by now.
-  e = xtx_impl<float>(Y, K, K, 1.0, hinv, ws, scratch, sm_count, st);
+  e = xtx_impl<float>(Y, K, K, 1.0, hinv, ws, scratch, sm_count, st, /*lower_tri=*/1);  // Y = L^-1 is lower triangular
   if (e != cudaSuccess) return e;
   if (info_out) {
     e = cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st);

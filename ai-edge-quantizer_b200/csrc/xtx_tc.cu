@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256)
 // overlaps the MMAs of the next.
 __global__ void __launch_bounds__(TC_THREADS, 1)
     xtx_tc_gemm(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                float* __restrict__ P, int K, int nkb, int nbj, int accumulate,
-                const int* __restrict__ flag) {
+                float* __restrict__ P, int K, int nkb_all, int nbj, int accumulate,
+                const int* __restrict__ flag, int tri) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   int bi, bj;
   tc_tile_index(blockIdx.x, nbj, bi, bj);
   const int i0 = bi * TC_BM, j0 = bj * TC_BN;
+  // tri: the input is LOWER TRIANGULAR as [contraction index t, column] (H^-1 = Y^T Y with Y = L^-1):
+  // Y[t, j] = 0 for t < j, so an (upper) output tile only sees contraction blocks from its first B
+  // column on (j0 >= i0) -- on average a third of the range.
+  const int kb0 = tri ? min(j0 / TC_BK, nkb_all - 1) : 0;
+  const int nkb = nkb_all - kb0;
   const int nseg = (nkb + TC_SEG_KB - 1) / TC_SEG_KB;
 
   if (warp == 0 && lane == 0) {
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
         uint8_t* base = smem + s * TC_STAGE_BYTES;
-        const int t = kb * TC_BK;
+        const int t = (kb0 + kb) * TC_BK;
         tma_load_2d(base, &tm_hi, t, i0, &full[s]);                                   // A hi
         tma_load_2d(base + TC_A_BYTES, &tm_lo, t, i0, &full[s]);                      // A lo
         tma_load_2d(base + 2 * TC_A_BYTES, &tm_hi, t, j0, &full[s]);                  // B hi
@@ -334,7 +339,7 @@ size_t xtx_tc_workspace_bytes(long long T, long long K) { return tc_layout(T, K)
 // values: then `out` was NOT written and the caller must run the SIMT path.
 template <typename OutT>
 cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha, OutT* out,
-                          void* ws, int sm_count, const int** flag_out, cudaStream_t st) {
+                          void* ws, int sm_count, const int** flag_out, cudaStream_t st, int lower_tri) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(xtx_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -358,6 +363,7 @@ cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha
   const unsigned tiles = static_cast<unsigned>(tc_tile_count(k));
   int launches = 0;
   int round = 0;
+  const int tri = (lower_tri && T == K && T <= l.chunk) ? 1 : 0;  // one chunk: block index == contraction index
   for (long long t0 = 0; t0 < T; t0 += l.chunk, ++round) {
     const long long tokens = T - t0 < l.chunk ? T - t0 : l.chunk;
     const long long used = round_up(tokens, TC_BK);  // pad columns up to `used` are zeroed
@@ -365,7 +371,7 @@ cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha
     xtx_split_transpose<<<sgrid, 256, 0, st>>>(x + t0 * K, tokens, k, l.pitch, hi, lo, flag);
     xtx_tc_gemm<<<tiles, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, P, k,
                                                           static_cast<int>(used / TC_BK), nbj,
-                                                          round > 0 ? 1 : 0, flag);
+                                                          round > 0 ? 1 : 0, flag, tri);
     launches += 2;
   }
   xtx_tc_finish<OutT><<<sm_count * 8, 256, 0, st>>>(P, k, alpha, out, flag);
@@ -375,8 +381,8 @@ cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha
 }
 
 template cudaError_t launch_xtx_tc<double>(const float*, long long, long long, double, double*,
-                                           void*, int, const int**, cudaStream_t);
+                                           void*, int, const int**, cudaStream_t, int);
 template cudaError_t launch_xtx_tc<float>(const float*, long long, long long, double, float*, void*,
-                                          int, const int**, cudaStream_t);
+                                          int, const int**, cudaStream_t, int);
 
 }  // namespace aeqb

@@ -113,15 +113,20 @@ def _hessian_f64(x, num_samples):
 
 
 @pytest.mark.parametrize("k,tokens", [(4096, 16384), (11008, 16384)])
-@pytest.mark.parametrize("two_level", ["0", "1000000"])
+@pytest.mark.parametrize("two_level", ["dmma", "0", "1000000"])
 def test_hessian_inverse_at_layer_size(cuda, monkeypatch, k, tokens, two_level):
-  """Both Cholesky variants at the Llama-7B orders: the float32 inverse against the damped
-  float64 Hessian it was computed from."""
+  """Every Cholesky variant at the Llama-7B orders (DMMA + lookahead: the default and the one the
+  bench times; two-level SIMT; single-level): the float32 inverse against the damped float64
+  Hessian it was computed from."""
   import torch
   from aeq_b200 import device
-  if k == 11008 and two_level != "0":
+  if k == 11008 and two_level == "1000000":
     pytest.skip("the single-level Cholesky is the small-K variant; K = 4096 covers it")
-  monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", two_level)
+  if two_level == "dmma":
+    monkeypatch.setenv("AEQB_CHOL_DMMA_MIN_K", "0")
+  else:
+    monkeypatch.setenv("AEQB_CHOL_DMMA_MIN_K", "1000000")
+    monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", two_level)
   g = torch.Generator(device=cuda).manual_seed(k)
   x = torch.randn(tokens, k, device=cuda, generator=g)
   x *= 1.0 + (torch.arange(k, device=cuda) % 7).float()  # anisotropic input features

@@ -177,9 +177,10 @@ def test_hessian_inverse_golden(cuda):
     np.testing.assert_array_equal(hd2.cpu().numpy(), h)
 
 
-@pytest.mark.parametrize("k", [3, 31, 64, 65, 200, 1024])
+@pytest.mark.parametrize("k", [3, 31, 64, 65, 127, 128, 129, 200, 257, 383, 1024, 1161])
 def test_hessian_inverse_property(cuda, k):
-  """H_damped @ Hinv == I for block-edge orders (diag block 32 / 64 boundaries, padding)."""
+  """H_damped @ Hinv == I for block-edge orders (32 / 64 / 128 block boundaries, padding, odd K:
+  the 8-byte cp.async path of chol_dmma.cu)."""
   import torch
   from aeq_b200 import device
   x = O.synthetic_activation((4, max(2 * k, 64), k), k)
@@ -196,13 +197,20 @@ def test_hessian_inverse_property(cuda, k):
 
 
 @pytest.mark.parametrize("k", [31, 64, 200, 1024])
-@pytest.mark.parametrize("min_k", ["0", "1000000"])
+@pytest.mark.parametrize("min_k", ["0", "1000000", "dmma", "dmma-serial"])
 def test_hessian_inverse_both_cholesky_variants(cuda, monkeypatch, k, min_k):
-  """The two-level Cholesky (rank-128 trailing updates, left-looking panels: the default) and the
-  single-level one (AEQB_CHOL_TWO_LEVEL_MIN_K above K) meet the same bars."""
+  """Every Cholesky variant meets the same bars: the DMMA / lookahead one (chol_dmma.cu, the
+  default; also with the lookahead stream switched off), the two-level SIMT one (rank-128 trailing
+  updates, left-looking panels) and the single-level one (AEQB_CHOL_TWO_LEVEL_MIN_K above K)."""
   import torch
   from aeq_b200 import device
-  monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", min_k)
+  if min_k.startswith("dmma"):
+    monkeypatch.setenv("AEQB_CHOL_DMMA_MIN_K", "0")
+    if min_k == "dmma-serial":
+      monkeypatch.setenv("AEQB_CHOL_NO_LOOKAHEAD", "1")
+  else:
+    monkeypatch.setenv("AEQB_CHOL_DMMA_MIN_K", "1000000")
+    monkeypatch.setenv("AEQB_CHOL_TWO_LEVEL_MIN_K", min_k)
   x = O.synthetic_activation((4, max(2 * k, 64), k), k + 1)
   h = O.gptq_hessian(x)
   if k == 31:
