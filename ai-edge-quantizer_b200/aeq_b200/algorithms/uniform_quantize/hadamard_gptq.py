@@ -61,6 +61,61 @@ def quantize_device(w_dev, hessian, num_bits: int, symmetric: bool = True,
   return q, scale, zp, n
 
 
+def quantize_layer_device(weights, feeds, hessians, num_bits: int, symmetric: bool = True,
+                          max_hadamard_size: Optional[int] = None, damp: float = 0.01,
+                          concurrent: bool = True):
+  """Rotated GPTQ of all the FC weights of one layer: [(q, scale, zero_point, hadamard_size)].
+
+  weights:  device float32 [R_i, K_i] matrices (e.g. q, k, v, o, gate, up, down of a decoder layer);
+  feeds:    for each weight, the key of the Hessian of ITS input in `hessians`;
+  hessians: {key: UNROTATED float64 [K, K] device Hessian} (shared by the weights it feeds).
+  The weights of a layer are independent problems given their Hessians (the reference walks them
+  one op at a time, params_generator.py:110-183, with no state in between), and both halves of the
+  work are chains of short dependent launches — the factorisation's diagonal blocks, the OBS
+  loop's 64-column steps — that leave most of the GPU idle.  So every Hessian is rotated, inverted
+  and every OBS loop runs on its OWN stream: the inverses overlap each other, an OBS loop starts
+  as soon as its inverse is there.  Same kernels, same launches per problem, same results as
+  `quantize_device` one weight at a time; concurrent=False runs exactly that, for A/B timing."""
+  import torch
+  from ... import device
+  main = torch.cuda.current_stream()
+  keys = list(dict.fromkeys(feeds))
+  rot = []
+  for w in weights:
+    r, n = hadamard_rotation.rotate_with_diagonal_hadamard_device(w, tuple(w.shape), max_hadamard_size)
+    rot.append((r, n))
+  hinv, infos, done = {}, [], {}
+  for key in keys:
+    n = hadamard_rotation.hadamard_size_for(int(hessians[key].shape[0]), max_hadamard_size)
+    s = torch.cuda.Stream() if concurrent else main
+    s.wait_stream(main)
+    with torch.cuda.stream(s):
+      h_rot = rotate_hessian_device(hessians[key], n)
+      hi, info = device.hessian_inverse(h_rot, damp, check=False)
+    hinv[key], done[key] = hi, s
+    infos.append(info)
+  out = []
+  streams = []
+  for (r, n), key in zip(rot, feeds):
+    s = torch.cuda.Stream() if concurrent else main
+    s.wait_stream(main)
+    s.wait_stream(done[key])
+    with torch.cuda.stream(s):
+      mn, mx, _ = device.row_stats(r)
+      zp, scale, _ = device.scale_zp_from_minmax(mn, mx, num_bits, symmetric, False)
+      q = device.gptq_quantize(r, hinv[key], scale.reshape(-1), zp.reshape(-1), 0, num_bits, symmetric)
+    for t in (q, scale, zp):
+      t.record_stream(main)
+    hinv[key].record_stream(s)
+    out.append((q, scale, zp, n))
+    streams.append(s)
+  for s in streams + list(done.values()):
+    main.wait_stream(s)
+  for info in infos:  # one read-back each, after everything is queued
+    device.check_hessian_info(info)
+  return out
+
+
 def get_tensor_quant_params(
     op_info: qtyping.OpInfo,
     tensor_quant_config: qtyping.TensorQuantizationConfig,

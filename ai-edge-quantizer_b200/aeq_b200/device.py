@@ -479,11 +479,13 @@ def xtx(x: torch.Tensor, alpha: float) -> torch.Tensor:
 
 
 def hessian_inverse(hessian: torch.Tensor, damp: float = 0.01,
-                    keep_damped_diagonal: bool = False) -> torch.Tensor:
+                    keep_damped_diagonal: bool = False, check: bool = True):
   """float32 inverse of the damped float64 Hessian (aeqb_hessian_inverse_f64).
 
   Raises numpy.linalg.LinAlgError like np.linalg.cholesky when the damped matrix is not
-  positive definite (this reads one int back, i.e. synchronises)."""
+  positive definite (this reads one int back, i.e. synchronises).  check=False defers that:
+  the call only enqueues work and returns (hinv, info) — `check_hessian_info(info)` raises later,
+  after the caller has queued whatever it wants to overlap (quantize_layer_device)."""
   import numpy as np
   if not hessian.is_cuda or hessian.dtype != torch.float64 or hessian.dim() != 2:
     raise ValueError("expected a float64 CUDA matrix")
@@ -496,9 +498,17 @@ def hessian_inverse(hessian: torch.Tensor, damp: float = 0.01,
   info = torch.zeros(1, dtype=torch.int32, device=hessian.device)
   _lib.call("aeqb_hessian_inverse_f64", _ptr(hessian), k, float(damp), int(keep_damped_diagonal),
             _ptr(hinv), _ptr(ws), _ptr(info), _stream())
+  if not check:
+    return hinv, info
+  check_hessian_info(info)
+  return hinv
+
+
+def check_hessian_info(info: torch.Tensor) -> None:
+  """Raises numpy.linalg.LinAlgError if the factorisation behind `info` met a non-positive pivot."""
+  import numpy as np
   if int(info.item()) != 0:
     raise np.linalg.LinAlgError("Matrix is not positive definite")
-  return hinv
 
 
 def gptq_quantize(w: torch.Tensor, hinv: torch.Tensor, scale: torch.Tensor,

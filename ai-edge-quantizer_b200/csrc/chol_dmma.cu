@@ -337,17 +337,24 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 #undef AEQB_TICK
 }
 
+// Column tiles (BN wide, indices in [tc_lo, tc_hi) relative to the trailing matrix) of row tile tr (BM
+// rows) that hold an element on or below the diagonal.
+__host__ __device__ inline int nt_tiles_in_row(int tr, int bm, int bn, int tc_lo, int tc_hi) {
+  const int last = (tr * bm + bm - 1) / bn + 1;  // column tiles [0, last) touch the triangle
+  const int hi = last < tc_hi ? last : tc_hi;
+  return hi > tc_lo ? hi - tc_lo : 0;
+}
+
 // ------------------------------------------------------------------ NT tile product on DMMA
 // acc[BM x 128] = sum_{k < depth} X[xrow0 + i][k] * Y[yrow0 + j][k]   (X, Y row-major, K-major rows)
 // MODE 0 (panel):   A[xrow0 + i][ocol0 + j]  = acc          (X = A[:, J:], Y = Linv)
 // MODE 1 (update):  A[xrow0 + i][yrow0 + j] -= acc, j-th column <= row only   (X = Y = A[:, J:])
 template <int MF, int NF, int WM, int WN, int MODE, int CPB>
-__global__ void __launch_bounds__(WM * WN * 32, (MF * WM * 8 >= 128) ? 1 : 2)
+__global__ void __launch_bounds__(WM * WN * 32, (MF * WM * NF * WN * 64 >= 128 * 128) ? 1 : 2)
     chol_nt(double* __restrict__ A, int K, const double* __restrict__ X, long long ldx, const double* __restrict__ Y,
-            long long ldy, int y_rows, int depth, int base, int ocol0, int tc_first, int tc_count) {
+            long long ldy, int y_rows, int depth, int base, int ocol0, int tc_lo, int tc_hi) {
   constexpr int BM = MF * WM * 8, BN = NF * WN * 8;
   constexpr int NT_THREADS = WM * WN * 32;
-  static_assert(BN == 128, "tile shape");
   extern __shared__ __align__(16) double nsm[];
   double* Xs = nsm;                          // [2][BM][KLD]
   double* Ys = nsm + 2 * BM * KLD;           // [2][BN][KLD]
@@ -360,26 +367,42 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * 8 >= 128) ? 1 : 2)
     xrow0 = static_cast<long long>(base) + static_cast<long long>(blockIdx.x) * BM;
     yrow0 = 0;
   } else {
-    // blockIdx.x enumerates (tr, tc) with tc in [tc_first, tc_first + tc_count), tr * BM rows >= tc * 128 columns
-    // row tiles of BM rows, column tiles of 128: a row tile is needed when its last row >= first column
-    const int per = 128 / BM;  // row tiles per column tile (1 or 4)
-    int tc = tc_first, left = blockIdx.x;
-    if (tc_count == 1) {
-      tc = tc_first;
+    // blockIdx.x enumerates, row tile by row tile (BM rows), the column tiles (BN columns, indices
+    // [tc_lo, tc_hi) relative to `base`) that touch the lower triangle: tc * BN <= tr * BM + BM - 1.
+    int left = blockIdx.x, tr = 0, tc = tc_lo;
+    if (tc_hi - tc_lo == 1) {
+      tr = left;  // one column tile: every row tile has it
+      left = 0;
+    } else if (BM == 128 && BN == 64 && tc_lo == 2) {
+      // row tile tr holds column tiles 2 .. 2 tr + 1: tr (tr - 1) tiles lie before it.  Closed form
+      // instead of a walk over up to 85 row tiles (a quarter of this kernel's stall samples were the
+      // integer instructions of that walk).
+      tr = static_cast<int>((1.0f + sqrtf(1.0f + 4.0f * static_cast<float>(left))) * 0.5f);
+      while (tr * (tr - 1) > left) --tr;
+      while ((tr + 1) * tr <= left) ++tr;
+      left -= tr * (tr - 1);
     } else {
-      // rows tiles available for column tile c: those with tr >= c * per  -> count = nrt - c * per
-      const int nrt = (K - base + BM - 1) / BM;
-      for (;; ++tc) {
-        const int cnt = nrt - tc * per;
+      for (;; ++tr) {
+        const int cnt = nt_tiles_in_row(tr, BM, BN, tc_lo, tc_hi);
         if (left < cnt) break;
         left -= cnt;
       }
     }
-    const int tr = tc * per + left;
+    tc = tc_lo + left;
     xrow0 = static_cast<long long>(base) + static_cast<long long>(tr) * BM;
-    yrow0 = static_cast<long long>(base) + static_cast<long long>(tc) * 128;
+    yrow0 = static_cast<long long>(base) + static_cast<long long>(tc) * BN;
   }
   const long long x_rows = K;
+  if (MODE == 1 && BM == 128) {
+    // The C tile comes from HBM (the trailing matrix is far larger than L2): ask L2 for its lines
+    // now, so that the epilogue's loads find them there after the products instead of waiting for
+    // DRAM with nothing left to overlap (a fifth of the stall samples were those waits).
+    constexpr int LPRW = BN * 8 / 128;  // 128-byte lines per tile row
+    for (int e = tid; e < BM * LPRW; e += NT_THREADS) {
+      const long long gr = xrow0 + e / LPRW, gc = yrow0 + (e % LPRW) * 16;
+      if (gr < K && gc <= gr) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + gr * K + gc));
+    }
+  }
 
   auto load_stage = [&](int s, int k0) {
     double* xs = Xs + s * BM * KLD;
@@ -434,12 +457,12 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * 8 >= 128) ? 1 : 2)
     __syncthreads();  // the stage is free for the load of s + 2
   }
 
-  if constexpr (MODE == 1 && MF * WM * 8 == 128 && CPB == 16) {
+  if constexpr (MODE == 1 && BM == 128 && CPB == 16) {
     // Update epilogue through shared memory: the accumulators are parked in a [128][136] tile
     // (16-byte stores, conflict-free), then every thread issues its 32 independent 16-byte loads of
     // C (a warp covers 512 contiguous bytes of a row), subtracts and stores.  Straight from the
     // fragments every DADD waited for its own 8-byte load: two thirds of the kernel's stall samples.
-    constexpr int CLD = 136;
+    constexpr int CLD = BN + 8;  // 16-byte stores of a quarter warp fall in 8 distinct 16-byte banks
     double* Ct = nsm;
 #pragma unroll
     for (int i = 0; i < MF; ++i)
@@ -449,21 +472,23 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * 8 >= 128) ? 1 : 2)
         *reinterpret_cast<double2*>(Ct + r * CLD + c) = make_double2(acc[i][j][0], acc[i][j][1]);
       }
     __syncthreads();
-    constexpr int NB16 = (128 * 64) / (16 * NT_THREADS);  // batches of 16 chunks per thread: 2 (256 threads) or 1 (512)
+    constexpr int CPRW = BN / 2;                              // 16-byte chunks per tile row
+    constexpr int NB16 = (BM * CPRW) / (16 * NT_THREADS);     // batches of 16 chunks per thread
+    static_assert(NB16 * 16 * NT_THREADS == BM * CPRW, "chunks divide over the threads");
 #pragma unroll
     for (int b = 0; b < NB16; ++b) {
       double2 v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int id = (b * 16 + u) * NT_THREADS + tid;
-        const long long gr = xrow0 + (id >> 6), gc = yrow0 + (id & 63) * 2;
+        const long long gr = xrow0 + id / CPRW, gc = yrow0 + (id % CPRW) * 2;
         v[u] = make_double2(0.0, 0.0);
         if (gr < K && gc <= gr) v[u] = *reinterpret_cast<const double2*>(A + gr * K + gc);
       }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int id = (b * 16 + u) * NT_THREADS + tid;
-        const int row = id >> 6, cc = (id & 63) * 2;
+        const int row = id / CPRW, cc = (id % CPRW) * 2;
         const long long gr = xrow0 + row, gc = yrow0 + cc;
         if (gr < K && gc <= gr) {
           const double2 d = *reinterpret_cast<const double2*>(Ct + row * CLD + cc);
@@ -497,30 +522,40 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * 8 >= 128) ? 1 : 2)
 }
 
 struct SideStream {
+  int dev = -1;
+  cudaStream_t caller = nullptr;
   cudaStream_t s = nullptr;
   cudaEvent_t panel = nullptr, rest = nullptr;
-  bool ok = false;
 };
 
-SideStream* side_stream() {
-  static SideStream per_dev[64];
+// One low-priority side stream (and its two events) per (device, caller stream): factorisations
+// that the caller runs concurrently on different streams (the four Hessians of a decoder layer)
+// keep independent lookahead queues.  Created on first use, kept for the life of the process; when
+// the table is full the factorisation simply runs without lookahead.
+SideStream* side_stream(cudaStream_t caller) {
+  constexpr int kMax = 32;
+  static SideStream table[kMax];
+  static int used = 0;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& ss = per_dev[dev];
-  if (!ss.ok) {
-    int lo = 0, hi = 0;
-    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.panel, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.rest, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ss.ok = true;
-  }
-  return &ss;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (int i = 0; i < used; ++i)
+    if (table[i].dev == dev && table[i].caller == caller) return &table[i];
+  if (used == kMax) return nullptr;
+  SideStream ss;
+  ss.dev = dev;
+  ss.caller = caller;
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.panel, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.rest, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  table[used] = ss;
+  return &table[used++];
 }
 
 template <int MF, int NF, int WM, int WN, int MODE, int CPB>
 cudaError_t configure_nt() {
-  constexpr size_t smem = static_cast<size_t>(2) * (MF * WM * 8 + 128) * KLD * 8;
+  constexpr size_t smem = static_cast<size_t>(2) * (MF * WM * 8 + NF * WN * 8) * KLD * 8;
   return cudaFuncSetAttribute(chol_nt<MF, NF, WM, WN, MODE, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(smem));
 }
@@ -538,13 +573,13 @@ cudaError_t cholesky_dmma_impl(double* A, int K, double* linv, int* info, cudaSt
   if (!nt_configured) {
     if ((e = configure_nt<4, 2, 1, 8, 0, CPB>()) != cudaSuccess) return e;
     if ((e = configure_nt<4, 2, 1, 8, 1, CPB>()) != cudaSuccess) return e;
-    if ((e = configure_nt<4, 4, 4, 4, 1, CPB>()) != cudaSuccess) return e;
+    if ((e = configure_nt<4, 4, 4, 2, 1, CPB>()) != cudaSuccess) return e;
     nt_configured = true;
   }
   constexpr size_t smem32 = static_cast<size_t>(2) * (32 + 128) * KLD * 8;
-  constexpr size_t smem128 = static_cast<size_t>(2) * (128 + 128) * KLD * 8;
+  constexpr size_t smem128 = static_cast<size_t>(2) * (128 + 64) * KLD * 8;  // 128 x 64 tiles
   const bool lookahead = getenv("AEQB_CHOL_NO_LOOKAHEAD") == nullptr;
-  SideStream* ss = lookahead ? side_stream() : nullptr;
+  SideStream* ss = lookahead ? side_stream(st) : nullptr;
   bool rest_pending = false;
   const double* AJ;
   for (int J = 0; J < K; J += DNB) {
@@ -577,20 +612,24 @@ cudaError_t cholesky_dmma_impl(double* A, int K, double* linv, int* info, cudaSt
       if ((e = cudaEventRecord(ss->panel, st)) != cudaSuccess) return e;
       if (rest_pending && (e = cudaStreamWaitEvent(st, ss->rest, 0)) != cudaSuccess) return e;
     }
-    // first tile column (the next block's diagonal and panel): 32-row tiles, on the caller's stream
+    // first 128 columns of the trailing matrix (the next block's diagonal and panel): 32-row tiles,
+    // on the caller's stream
     chol_nt<4, 2, 1, 8, 1, CPB><<<(below + 31) / 32, 256, smem32, st>>>(
         A, K, AJ, K, AJ, K, K, DNB, base, 0, 0, 1);
     ++*launches;
     if (nct > 1) {
-      // remaining tile columns: 128 x 128 tiles; tiles of column c: row tiles c .. nct - 1
-      const int ntiles = (nct - 1) * nct / 2;
+      // the other columns: 128 x 64 tiles, two CTAs per SM (one tile's prologue and epilogue overlap
+      // the other's products)
+      const int nrt = nct, ntc = (below + 63) / 64;
+      long long ntiles = 0;
+      for (int tr = 0; tr < nrt; ++tr) ntiles += nt_tiles_in_row(tr, 128, 64, 2, ntc);
       cudaStream_t rs = st;
       if (ss != nullptr) {
         rs = ss->s;
         if ((e = cudaStreamWaitEvent(rs, ss->panel, 0)) != cudaSuccess) return e;
       }
-      chol_nt<4, 4, 4, 4, 1, CPB><<<ntiles, 512, smem128, rs>>>(
-          A, K, AJ, K, AJ, K, K, DNB, base, 0, 1, nct - 1);
+      chol_nt<4, 4, 4, 2, 1, CPB><<<static_cast<unsigned>(ntiles), 256, smem128, rs>>>(
+          A, K, AJ, K, AJ, K, K, DNB, base, 0, 2, ntc);
       ++*launches;
       if (ss != nullptr) {
         if ((e = cudaEventRecord(ss->rest, rs)) != cudaSuccess) return e;

@@ -753,8 +753,8 @@ def run_gptq(ctx, steps, warmup):
     for name, k in LLAMA_INPUTS:
       xs[(l, name)] = torch.randn(t_local, k, device=dev, generator=gen)
   num_samples = 128  # sequences per Hessian (alpha = 2 / num_samples, gptq.py:105)
-  parts = {"hessian": 0.0, "exchange": 0.0, "rotate": 0.0, "inverse": 0.0, "obs_loop": 0.0}
-  ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+  parts = {"hessian": 0.0, "exchange": 0.0, "quantize": 0.0}
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
   state = {}
 
   def step():
@@ -773,36 +773,34 @@ def run_gptq(ctx, steps, warmup):
       mine[name] = hs[(rank, name)]
     del hs
     ev[2].record()
-    hinv, rot = {}, []
-    for name, k in LLAMA_INPUTS:
-      n = hadamard_gptq.hadamard_rotation.hadamard_size_for(k, 4096)
-      mine[name] = hadamard_gptq.rotate_hessian_device(mine[name], n)
-    for w in layer:
-      n = hadamard_gptq.hadamard_rotation.hadamard_size_for(w.shape[1], 4096)
-      rot.append(device.hadamard_rows(w, n))
+    # rotate W and H, invert, OBS loops: the layer's seven problems on their own streams
+    res = hadamard_gptq.quantize_layer_device(layer, LLAMA_FEEDS, mine, 4, True, 4096, 0.01,
+                                              concurrent=not os.environ.get("AEQB_BENCH_GPTQ_SERIAL"))
     ev[3].record()
-    for name, k in LLAMA_INPUTS:
-      hinv[name] = device.hessian_inverse(mine[name], 0.01)
-    ev[4].record()
-    qs = []
-    for r, feed in zip(rot, LLAMA_FEEDS):
-      mn, mx, _ = device.row_stats(r)
-      zp, scale, _ = device.scale_zp_from_minmax(mn, mx, 4, True, False)
-      qs.append((device.gptq_quantize(r, hinv[feed], scale.reshape(-1), None, 0, 4, True), scale))
-    ev[5].record()
-    state["q"], state["rot"], state["hinv"] = qs, rot, hinv
+    state["res"], state["h"] = res, mine
 
   ms, launches, per_rank = ctx.timed(step, steps, warmup)
   torch.cuda.synchronize()
-  for key, i in (("hessian", 0), ("exchange", 1), ("rotate", 2), ("inverse", 3), ("obs_loop", 4)):
+  for key, i in (("hessian", 0), ("exchange", 1), ("quantize", 2)):
     parts[key] = ev[i].elapsed_time(ev[i + 1])
+  # the same seven problems one after the other on one stream (what the concurrency buys)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  hadamard_gptq.quantize_layer_device(layer, LLAMA_FEEDS, state["h"], 4, True, 4096, 0.01, concurrent=False)
+  e1.record()
+  torch.cuda.synchronize()
+  ms_serial = e0.elapsed_time(e1)
   # sanity of the timed outputs: proxy loss of the o-projection against plain rounding of the same
   # rotated weight (GPTQ must win), and H_rot @ Hinv = I
-  q, scale = state["q"][3]
-  r = state["rot"][3]
-  hi = state["hinv"]["attn_out"].double()
+  q, scale, _, n_o = state["res"][3]
+  r = device.hadamard_rows(layer[3], n_o)
+  h_rot = hadamard_gptq.rotate_hessian_device(state["h"]["attn_out"], n_o)
+  d = torch.diagonal(h_rot)
+  d = torch.where(d == 0, torch.ones_like(d), d)
+  hd = h_rot.clone()
+  hd.diagonal().copy_(d + 0.01 * d.mean())  # the damped rotated Hessian (gptq.py:111-118)
   rtn = torch.clamp(torch.round(r / scale), -8, 7)
-  hd = torch.linalg.inv(hi)  # the damped rotated Hessian the inverse stands for
 
   def loss(qq):
     e = r.double() - qq.double() * scale.double()
@@ -812,8 +810,10 @@ def run_gptq(ctx, steps, warmup):
           "launches_per_step": launches / steps, "layers": world, "tokens_per_hessian": tokens,
           "tokens_per_rank_per_hessian": t_local, "fp32_bytes": world * lbytes,
           "scaling": "weak (one Llama-7B decoder layer = 7 FC weights per GPU)",
-          "ms_hessians": parts["hessian"], "ms_exchange": parts["exchange"], "ms_rotate": parts["rotate"],
-          "ms_inverse_4x": parts["inverse"], "ms_obs_loop_7x": parts["obs_loop"],
+          "ms_hessians": parts["hessian"], "ms_exchange": parts["exchange"],
+          "ms_rotate_inverse_obs": parts["quantize"], "ms_rotate_inverse_obs_one_stream": ms_serial,
+          "concurrency": "4 rotated-Hessian inverses and 7 OBS loops on their own streams"
+                         " (hadamard_gptq.quantize_layer_device)",
           "hessian_tflops_fp32_equivalent": 2.0 * t_local * world * sum(k * k for _, k in LLAMA_INPUTS) / parts["hessian"] / 1e9,
           "proxy_loss_vs_round_to_nearest": l_gptq / l_rtn, "parity_checked": bool(l_gptq < l_rtn),
           "exchange": "none (N=1)" if world == 1 else

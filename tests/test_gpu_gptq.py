@@ -479,3 +479,26 @@ def test_lane_per_row_column_kernel_equals_the_row_per_warp_one(cuda, monkeypatc
                                torch.from_numpy(zp.astype(np.int32).reshape(-1)).to(cuda), 0, 4, sym).cpu().numpy()
     np.testing.assert_array_equal(got[:, :64], want[:, :64])
     assert (got != want).mean() <= 5e-3
+
+
+def test_layer_level_concurrent_gptq_equals_one_weight_at_a_time(cuda):
+  """hadamard_gptq.quantize_layer_device (every Hessian inverse and OBS loop on its own stream, the
+  lookahead Cholesky keeping one side stream per caller stream) returns exactly what
+  quantize_device returns for each weight alone: same kernels, same launches per problem."""
+  import torch
+  from aeq_b200.algorithms.uniform_quantize import hadamard_gptq
+  shapes = [(96, 512), (64, 512), (160, 512), (64, 384), (200, 384)]
+  feeds = ["a", "a", "a", "b", "b"]
+  ws = [torch.from_numpy(O.synthetic_weight(r, k, 40 + i)).to(cuda) for i, (r, k) in enumerate(shapes)]
+  hs = {"a": torch.from_numpy(O.gptq_hessian(O.synthetic_activation((4, 300, 512), 7))).to(cuda),
+        "b": torch.from_numpy(O.gptq_hessian(O.synthetic_activation((4, 300, 384), 8))).to(cuda)}
+  for concurrent in (True, False):
+    got = hadamard_gptq.quantize_layer_device(ws, feeds, hs, 4, True, 128, concurrent=concurrent)
+    torch.cuda.synchronize()
+    for w, f, (q, scale, zp, n) in zip(ws, feeds, got):
+      wq, wscale, wzp, wn = hadamard_gptq.quantize_device(w, hs[f], 4, True, 128)
+      assert n == wn == 128
+      assert torch.equal(q, wq) and torch.equal(scale, wscale) and torch.equal(zp, wzp)
+  bad = {"a": -torch.eye(512, dtype=torch.float64, device=cuda), "b": hs["b"]}
+  with pytest.raises(np.linalg.LinAlgError):
+    hadamard_gptq.quantize_layer_device(ws, feeds, bad, 4, True, 128)
