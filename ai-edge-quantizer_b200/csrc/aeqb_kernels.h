@@ -184,7 +184,7 @@ cudaError_t launch_split_planes(const float* x, long long n, float* hi, float* l
 cudaError_t gptq_update_tc_prepare(GptqTcMapsOpaque* out, const float* err_hi, const float* err_lo,
                                    const float* h_hi, const float* h_lo, long long R, long long K);
 cudaError_t launch_gptq_update_tc(const GptqTcMapsOpaque* maps, float* part, long long R, int c0, int L,
-                                  int n_splits, cudaStream_t st);
+                                  int n_splits, cudaStream_t st, int light = 0);
 
 // Unfused element-wise pieces (elementwise.cu).
 cudaError_t launch_scale_zp(const float* mn, const float* mx, const float* clip, long long n,

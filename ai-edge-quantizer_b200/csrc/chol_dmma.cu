@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * NF * WN * 64 >= 128 *
     // blockIdx.x enumerates, row tile by row tile (BM rows), the column tiles (BN columns, indices
     // [tc_lo, tc_hi) relative to `base`) that touch the lower triangle: tc * BN <= tr * BM + BM - 1.
     int left = blockIdx.x, tr = 0, tc = tc_lo;
-    if (tc_hi - tc_lo == 1) {
-      tr = left;  // one column tile: every row tile has it
+    if (tc_lo == 0 && tc_hi == 1) {
+      tr = left;  // the first column tile: every row tile has it
       left = 0;
     } else if (BM == 128 && BN == 64 && tc_lo == 2) {
       // row tile tr holds column tiles 2 .. 2 tr + 1: tr (tr - 1) tiles lie before it.  Closed form

@@ -37,7 +37,7 @@ constexpr int GU_STAGES = 4;
 constexpr uint32_t GU_A_BYTES = GU_BM * GU_BK * 4;   // 16 KiB per plane
 constexpr uint32_t GU_B_BYTES = GU_BN * GU_BK * 4;   // 8 KiB per plane
 constexpr uint32_t GU_STAGE_BYTES = 2 * GU_A_BYTES + 2 * GU_B_BYTES;  // 48 KiB
-constexpr uint32_t GU_SMEM_BYTES = GU_STAGES * GU_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t gu_smem_bytes(int stages) { return stages * GU_STAGE_BYTES + 1024 + 256; }
 constexpr int GU_EPI_WARPS = 4;
 constexpr int GU_THREADS = (2 + GU_EPI_WARPS) * 32;
 constexpr int GU_SEG_KB = 4;   // stages per accumulation segment (128 contraction values)
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // part[blockIdx.y][r, c] = sum_{l in this split} Err[r, l] * Hinv[c0 + c, l]
+template <int STAGES>
 __global__ void __launch_bounds__(GU_THREADS, 1)
     gptq_update_tc_kernel(const __grid_constant__ CUtensorMap tm_ehi, const __grid_constant__ CUtensorMap tm_elo,
                           const __grid_constant__ CUtensorMap tm_hhi, const __grid_constant__ CUtensorMap tm_hlo,
@@ -69,9 +70,9 @@ __global__ void __launch_bounds__(GU_THREADS, 1)
   extern __shared__ uint8_t gu_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(gu_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GU_STAGES * GU_STAGE_BYTES);
-  uint64_t* empty = full + GU_STAGES;
-  uint64_t* tmem_full = empty + GU_STAGES;   // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * GU_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_elo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hlo)) : "memory");
-    for (int s = 0; s < GU_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(GU_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % GU_STAGES;
-        const uint32_t ph = static_cast<uint32_t>(kb / GU_STAGES) & 1u;
+        const int s = kb % STAGES;
+        const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], GU_STAGE_BYTES);
         uint8_t* base = smem + s * GU_STAGE_BYTES;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(GU_THREADS, 1)
         const int kb_end = min(nkb, kb + GU_SEG_KB);
         bool first = true;
         for (; kb < kb_end; ++kb) {
-          const int s = kb % GU_STAGES;
-          const uint32_t ph = static_cast<uint32_t>(kb / GU_STAGES) & 1u;
+          const int s = kb % STAGES;
+          const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + s * GU_STAGE_BYTES);
@@ -251,8 +252,11 @@ cudaError_t gptq_update_tc_prepare(GptqTcMapsOpaque* out, const float* err_hi, c
   GptqTcMaps* m = reinterpret_cast<GptqTcMaps*>(out);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gptq_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(GU_SMEM_BYTES));
+    cudaError_t e = cudaFuncSetAttribute(gptq_update_tc_kernel<GU_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(gu_smem_bytes(GU_STAGES)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gptq_update_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(gu_smem_bytes(2)));
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -263,12 +267,19 @@ cudaError_t gptq_update_tc_prepare(GptqTcMapsOpaque* out, const float* err_hi, c
 }
 
 // part[s][R][64] = split s of  Err[:, :L] @ Hinv[:L, c0 : c0 + 64]   (L a multiple of 64).
+// light: two pipeline stages (97 KiB of shared memory instead of 193) so that the column kernel's CTAs
+// fit beside it on the same SMs — the lookahead runs this product WHILE the previous block's columns
+// are being quantised.
 cudaError_t launch_gptq_update_tc(const GptqTcMapsOpaque* maps, float* part, long long R, int c0, int L,
-                                  int n_splits, cudaStream_t st) {
+                                  int n_splits, cudaStream_t st, int light) {
   const GptqTcMaps* m = reinterpret_cast<const GptqTcMaps*>(maps);
   const dim3 grid(static_cast<unsigned>((R + GU_BM - 1) / GU_BM), static_cast<unsigned>(n_splits));
-  gptq_update_tc_kernel<<<grid, GU_THREADS, GU_SMEM_BYTES, st>>>(m->ehi, m->elo, m->hhi, m->hlo, part,
-                                                                 static_cast<int>(R), c0, L / GU_BK);
+  if (light)
+    gptq_update_tc_kernel<2><<<grid, GU_THREADS, gu_smem_bytes(2), st>>>(m->ehi, m->elo, m->hhi, m->hlo, part,
+                                                                        static_cast<int>(R), c0, L / GU_BK);
+  else
+    gptq_update_tc_kernel<GU_STAGES><<<grid, GU_THREADS, gu_smem_bytes(GU_STAGES), st>>>(
+        m->ehi, m->elo, m->hhi, m->hlo, part, static_cast<int>(R), c0, L / GU_BK);
   return count_launch();
 }
 
