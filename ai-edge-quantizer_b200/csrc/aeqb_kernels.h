@@ -65,6 +65,7 @@ struct RowsBatch {
   const long long* table_ends;  // tile_end of every table entry, packed (16 per 128-byte line): the
                                 // producer's walk over hundreds of small tensors reads these, not the jobs
   int rich;
+  int one_poller;  // AEQB_ROWS_ONE_POLLER: only consumer warp 0 polls the full barrier, the others park on a named barrier
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
 int rows_job_class(const RowsJob& j, int bits);

@@ -30,6 +30,7 @@ namespace aeqb {
 namespace {
 
 constexpr int kMaxRowsPerTile = 64;
+constexpr int kRowsOnePollerDefault = 0;
 constexpr int kChunk = 128;   // floats per warp chunk
 
 struct RowAcc {  // merged across warps with shared-memory atomics
@@ -252,7 +253,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1
     if (++buf == 3) buf = 0;
     const float4* t4 = reinterpret_cast<const float4*>(smem_raw + static_cast<size_t>(s) * STAGE_BYTES);
 
-    mbar_wait(&full_bar[s], ph);
+    if (b.one_poller) {
+      // One warp polls the mbarrier; the others wait on a hardware named barrier, which issues
+      // nothing while it blocks (the polling loops were a quarter of the executed instructions of
+      // the 477-tensor launch).  Their own wait afterwards succeeds at once: it is the acquire that
+      // makes the bulk copy's bytes visible to them.
+      if (warp == 0) mbar_wait(&full_bar[s], ph);
+      named_bar_sync(2, NW * 32);
+      if (warp != 0) mbar_wait(&full_bar[s], ph);
+    } else {
+      mbar_wait(&full_bar[s], ph);
+    }
 
     const RowsJob& job = desc[s].job;
     const long long row0 = desc[s].row0;
@@ -568,7 +579,14 @@ cudaError_t launch_stream_as(const RowsBatch& b, int sm_count, int ctas_per_sm, 
   }
   long long grid = static_cast<long long>(sm_count) * ctas_per_sm;
   if (grid > b.n_tiles) grid = b.n_tiles;
-  kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
+  static const int one_poller = getenv("AEQB_ROWS_ONE_POLLER") ? atoi(getenv("AEQB_ROWS_ONE_POLLER")) : kRowsOnePollerDefault;
+  if (b.one_poller != one_poller) {
+    RowsBatch bb = b;
+    bb.one_poller = one_poller;
+    kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(bb);
+  } else {
+    kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
+  }
   return count_launch();
 }
 

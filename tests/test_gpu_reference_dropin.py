@@ -299,3 +299,44 @@ def test_error_behaviour_through_the_reference_wrapper(R):
                                         r" divisible by block size 32"):
     _materialize(R, R.am.AlgorithmName.MIN_MAX_UNIFORM_QUANT, "FULLY_CONNECTED", op, graph,
                  _cfg(R, 4, "BLOCKWISE_32"), compute_precision=R.q.ComputePrecision.INTEGER)
+
+
+def test_histogram_calibration_registered_in_the_reference_registry(R):
+  """plugin.install_histogram: the reference's registry resolves our key for every op its min-max
+  algorithm covers; CALIBRATE returns the reference's min / max plus a histogram equal to the one the
+  reference's DynamicHistogram builds, the update func merges, and MATERIALIZE (the reference's
+  materialize_fc_conv over our adapted get_tensor_quant_params) quantises the weight exactly as the
+  reference's min-max algorithm does."""
+  ref_hu = refshim.ref("utils.histogram_utils")
+  key = R.plugin.install_histogram(R.am)
+  FC = R.q.TFLOperationName.FULLY_CONNECTED
+  assert R.am.is_op_registered(key, FC)
+  assert set(R.am.get_supported_ops(key)) == set(R.am.MIN_MAX_OP_NAME_MATERIALIZE_FUNC_DICT)
+  w = O.synthetic_weight(32, 256, 5)
+  op, graph = _graph(R, w, in_shape=(6, 40, 256), out_shape=(6, 40, 32))
+  x, y = O.synthetic_activation((6, 40, 256), 3), O.synthetic_activation((6, 40, 32), 4)
+  cal = R.am.get_quantization_func(key, FC, R.q.QuantizeMode.CALIBRATE)
+  want_mm = R.am.get_quantization_func(R.am.AlgorithmName.MIN_MAX_UNIFORM_QUANT, FC, R.q.QuantizeMode.CALIBRATE)(
+      op, graph, {"input": x, "output": y})
+  got = cal(op, graph, {"input": x, "output": y})
+  for name in ("input", "output"):
+    np.testing.assert_array_equal(got[name]["min"], want_mm[name]["min"])
+    np.testing.assert_array_equal(got[name]["max"], want_mm[name]["max"])
+  h = ref_hu.DynamicHistogram(max_tensor_bins=2048)
+  h.add(x)
+  np.testing.assert_array_equal(got["input"]["histogram"]["channels"][0]["hist_counts"],
+                                h.to_dict()["channels"][0]["hist_counts"])
+  upd = R.am.get_update_qsv_func(key, FC)
+  merged = upd(got["input"], cal(op, graph, {"input": x * 2, "output": y})["input"])
+  h2 = ref_hu.DynamicHistogram(max_tensor_bins=2048)
+  h2.add(x * 2)
+  h.merge(h2)  # the reference's resampled merge (it may drop a few counts to rounding: so does ours)
+  np.testing.assert_array_equal(merged["histogram"]["channels"][0]["hist_counts"],
+                                h.to_dict()["channels"][0]["hist_counts"])
+  # weight materialisation through the reference's own materialiser, against its min-max algorithm
+  op_cfg = dict(compute_precision=R.q.ComputePrecision.INTEGER)
+  want = _materialize(R, R.am.AlgorithmName.MIN_MAX_UNIFORM_QUANT, "FULLY_CONNECTED", op, graph,
+                      _cfg(R, 8, "CHANNELWISE"), **op_cfg)
+  got_p = _materialize(R, key, "FULLY_CONNECTED", op, graph, _cfg(R, 8, "CHANNELWISE"), **op_cfg)
+  assert set(got_p) == set(want)
+  _same_params(got_p["weight"].consumers[0].parameters, want["weight"].consumers[0].parameters)
