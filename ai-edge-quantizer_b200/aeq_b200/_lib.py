@@ -30,6 +30,7 @@ SIGNATURES = {
     "aeqb_launch_count": (_L, []),
     "aeqb_host_requant_rows_batch_f32": (_I, [_P, _L, _I, _I]),
     "aeqb_host_requant_blocks_batch_f32": (_I, [_P, _L, _I, _I]),
+    "aeqb_host_requant_mse_rows_batch_f32": (_I, [_P, _L, _I, _F]),
     "aeqb_host_set_devices": (_I, [_P, _I]),
     "aeqb_host_worker_threads": (_I, []),
     "aeqb_host_copy_in": (_I, [_P, _P, _c.c_size_t, _P]),

@@ -89,6 +89,27 @@ def requant_rows(ws: Sequence[np.ndarray], bits: int, symmetric: bool = True,
   return outs
 
 
+def requant_mse_rows(ws: Sequence[np.ndarray], bits: int, multiplier: float, want_packed: bool = False,
+                     outs=None, alloc=np.empty):
+  """MSE per channel (scale = multiplier * RMS(row), zero point 0) of host arrays through the same
+  pipeline; returns [(q, packed, scale[rows,1], zp[rows,1])].  Rows must hold a multiple of 128
+  values and at most 96 KiB (the fused kernel's RMS statistic)."""
+  _require_gpu()
+  ws = [_f32_2d(w) for w in ws]
+  if outs is None:
+    outs = []
+    for w in ws:
+      r, c = w.shape
+      outs.append((alloc((r, c), np.int8), alloc((r * c * bits // 8,), np.uint8) if want_packed else None,
+                   alloc((r, 1), np.float32), alloc((r, 1), np.int32)))
+  jobs = (_lib.RowsJob * len(ws))()
+  for i, (w, o) in enumerate(zip(ws, outs)):
+    jobs[i] = _lib.RowsJob(_p(w), w.shape[0], w.shape[1], None, _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]))
+  _lib.call("aeqb_host_requant_mse_rows_batch_f32", ctypes.cast(jobs, ctypes.c_void_p), len(ws), bits,
+            float(multiplier))
+  return outs
+
+
 def requant_blocks(ws: Sequence[np.ndarray], block: int, bits: int, want_q: bool = True,
                    want_packed: bool = False, want_scale: bool = True,
                    want_scale_f16: bool = False, outs=None, alloc=np.empty):

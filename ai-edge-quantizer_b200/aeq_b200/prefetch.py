@@ -37,12 +37,18 @@ def _default_params(**kw):
   return qtyping.UniformQuantParams(**kw)
 
 
+MSE_MULTIPLIERS = {8: 0.05408, 4: 0.37755}  # mse.py:30-33
+
+
 def prefetch_weights(items: Iterable, cache, make_params: Optional[Callable] = None,
-                     get_tensor_data: Optional[Callable] = None) -> dict:
+                     get_tensor_data: Optional[Callable] = None,
+                     algorithm: str = "min_max_uniform_quantize") -> dict:
   """Quantises the constant float32 weights of `items` and inserts them into `cache`.
 
-  items:   iterable of (op_info, graph_info) for ops whose algorithm is min-max uniform
-           quantisation (`op_info.op_quant_config.weight_tensor_config` is the tensor config).
+  items:   iterable of (op_info, graph_info) for ops whose algorithm is `algorithm`: min-max uniform
+           quantisation (default) or "MSE" (per-channel symmetric INT8 / INT4 with 128-multiple rows;
+           everything else is left to the per-op path)
+           (`op_info.op_quant_config.weight_tensor_config` is the tensor config).
   cache:   a TensorQuantParamsCache (ours or the reference's: `lookup` / `insert`).
   make_params: keyword factory for the UniformQuantParams class to emit (default: ours).
   Returns counters: tensors quantised, cache hits skipped, tensors left to the per-op path.
@@ -74,6 +80,14 @@ def prefetch_weights(items: Iterable, cache, make_params: Optional[Callable] = N
         continue
       block = uqt.extract_block_size_from_granularity(_gran(cfg))
       gran = _name(cfg.granularity)
+      if algorithm == "MSE":
+        cols = int(np.prod(data.shape[1:]))
+        if (block or gran != "CHANNELWISE" or not cfg.symmetric or cfg.num_bits not in MSE_MULTIPLIERS
+            or cols % 128 or cols * 4 > 98304):
+          stats["left_to_per_op_path"] += 1  # the per-op call handles (or rejects) these
+          continue
+        groups.setdefault(("mse", cfg.num_bits), []).append((tensor.buffer, cfg, data))
+        continue
       if block:
         if op not in _BLOCKWISE_OPS or not cfg.symmetric or data.shape[-1] % block:
           stats["left_to_per_op_path"] += 1  # the per-op call raises the reference's error
@@ -86,7 +100,18 @@ def prefetch_weights(items: Iterable, cache, make_params: Optional[Callable] = N
         continue
       groups.setdefault(gkey, []).append((tensor.buffer, cfg, data))
   for gkey, members in groups.items():
-    if gkey[0] == "rows":
+    if gkey[0] == "mse":
+      bits = gkey[1]
+      ws = [d.reshape(d.shape[0], -1) for _, _, d in members]
+      outs = host.requant_mse_rows(ws, bits, MSE_MULTIPLIERS[bits])
+      for (buf, cfg, d), (q, _, scale, _zp) in zip(members, outs):
+        pshape = [d.shape[0]] + [1] * (d.ndim - 1)
+        scale = scale.reshape(pshape)
+        cache.insert(buf, cfg, make_params(
+            num_bits=bits, quantized_dimension=0, scale=scale,
+            zero_point=np.zeros_like(scale, dtype=np.int32), symmetric=True,  # mse.py:109
+            quantized_data=q.reshape(d.shape), block_size=0))
+    elif gkey[0] == "rows":
       _, sym, bits = gkey
       ws = [d.reshape(d.shape[0], -1) for _, _, d in members]
       fuse_pack = bits in (2, 4) and all(w.shape[1] % (8 // bits) == 0 for w in ws)

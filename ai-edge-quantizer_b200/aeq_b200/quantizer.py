@@ -123,7 +123,7 @@ class Quantizer:
     # Batched driver first: every min-max weight of the model goes through
     # ONE pipelined host-buffer call per (granularity, bits) group and lands in the cache, so
     # the per-op walk below (params_generator.py:110-183) finds its constants already done.
-    items = []
+    items, mse_items = [], []
     for subgraph in model.subgraphs:
       graph_info = qtyping.GraphInfo(subgraph.tensors, model.buffers)
       for op_index, op in enumerate(subgraph.operators):
@@ -135,8 +135,13 @@ class Quantizer:
             op_name, fu.get_op_scope(op, subgraph.tensors))
         if alg == AlgorithmName.MIN_MAX_UNIFORM_QUANT.value and cfg.weight_tensor_config is not None:
           items.append((qtyping.OpInfo(op, op_name, op_index, cfg), graph_info))
+        elif alg == AlgorithmName.MSE.value and cfg.weight_tensor_config is not None:
+          mse_items.append((qtyping.OpInfo(op, op_name, op_index, cfg), graph_info))
     if items:
       self.prefetch_stats = prefetch.prefetch_weights(items, cache)
+    if mse_items:
+      st = prefetch.prefetch_weights(mse_items, cache, algorithm="MSE")
+      self.prefetch_stats = {k: self.prefetch_stats.get(k, 0) + v for k, v in st.items()}
     for sg_index, subgraph in enumerate(model.subgraphs):
       graph_info = qtyping.GraphInfo(subgraph.tensors, model.buffers)
       for op_index, op in enumerate(subgraph.operators):

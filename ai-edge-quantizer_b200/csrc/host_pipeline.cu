@@ -392,7 +392,7 @@ void drain_all() {
   cudaGetLastError();
 }
 
-int enqueue_chunk(Chunk& c, int mode, int bits, int symmetric, int block) {
+int enqueue_chunk(Chunk& c, int mode, int bits, int symmetric, int block, float mse_k) {
   const HostJob& hj = *c.job;
   Slot& s = *c.slot;
   const long long ne = c.nr * hj.cols;
@@ -413,9 +413,12 @@ int enqueue_chunk(Chunk& c, int mode, int bits, int symmetric, int block) {
     j.scale = s.d_scale; j.zp = s.d_zp;
     j.rows = c.nr; j.cols = static_cast<int>(hj.cols);
     j.mm_stride = j.clip_stride = j.out_stride = 1;
+    j.mse_k = mse_k;  // != 0: scale = k * RMS(row) (mse.py:100-108); rows stay independent, so chunking is exact
     const int klass = aeqb::rows_job_class(j, bits);
     cudaError_t e;
-    if (klass == 0) {
+    if (klass == 0 && mse_k != 0.0f) {
+      return aeqb::host_fail("MSE rows need a multiple of 128 columns and at most 96 KiB per row");
+    } else if (klass == 0) {
       e = aeqb::launch_requant_rows_generic(j, bits, symmetric, s.stream);
     } else {
       j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
@@ -458,7 +461,7 @@ int enqueue_chunk(Chunk& c, int mode, int bits, int symmetric, int block) {
 }
 
 // mode 0: per-channel rows kernel; mode 1: blockwise kernel.
-int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, int symmetric, int block) {
+int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, int symmetric, int block, float mse_k) {
   int home = 0;
   if (int rc = aeqb::host_check(cudaGetDevice(&home), "cudaGetDevice")) return rc;
   // ---- validate everything before anything is enqueued
@@ -470,6 +473,9 @@ int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, i
     if (mode == 0 && hj.packed && hj.cols % (8 / bits) != 0)
       return aeqb::host_fail("packed output of a [%lld, %lld] tensor would straddle rows; pack separately",
                              hj.rows, hj.cols);
+    if (mode == 0 && mse_k != 0.0f && (hj.cols % 128 != 0 || hj.cols * 4 > 98304))
+      return aeqb::host_fail("MSE rows need a multiple of 128 columns and at most 96 KiB per row, got %lld columns",
+                             hj.cols);
   }
   std::vector<int> devs = g_devices;
   if (devs.empty()) devs.push_back(home);
@@ -527,7 +533,7 @@ int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, i
       if (!chunks[a].staged) rc = prepare(a);
     if (rc) break;
     rc = aeqb::host_check(cudaSetDevice(chunks[k].ring->device), "cudaSetDevice");
-    if (!rc) rc = enqueue_chunk(chunks[k], mode, bits, symmetric, block);
+    if (!rc) rc = enqueue_chunk(chunks[k], mode, bits, symmetric, block, mse_k);
   }
   if (!rc) {
     for (Ring* r : rings) {
@@ -545,9 +551,9 @@ int run_host_locked(const HostJob* jobs, long long n_jobs, int mode, int bits, i
   return rc;
 }
 
-int run_host(const HostJob* jobs, long long n_jobs, int mode, int bits, int symmetric, int block) {
+int run_host(const HostJob* jobs, long long n_jobs, int mode, int bits, int symmetric, int block, float mse_k = 0.0f) {
   std::lock_guard<std::mutex> lock(g_mu);
-  return run_host_locked(jobs, n_jobs, mode, bits, symmetric, block);
+  return run_host_locked(jobs, n_jobs, mode, bits, symmetric, block, mse_k);
 }
 
 // ---------------------------------------------------------------- plain staged copies
@@ -703,6 +709,21 @@ int aeqb_host_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, 
     v[static_cast<size_t>(i)] = HostJob{a.x, a.rows, a.cols, a.q, a.packed, a.scale, a.zp, nullptr};
   }
   return run_host(v.data(), n_jobs, 0, bits, symmetric ? 1 : 0, 0);
+}
+
+int aeqb_host_requant_mse_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits, float k) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return aeqb::host_fail("bad job list");
+  if (bits != 4 && bits != 8) return aeqb::host_fail("unsupported num_bits %d (4 or 8)", bits);
+  if (!(k > 0.0f)) return aeqb::host_fail("the MSE multiplier must be positive");
+  std::vector<HostJob> v(static_cast<size_t>(n_jobs));
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const aeqb_rows_job& a = jobs[i];
+    if (a.clip) return aeqb::host_fail("clipping constants are not supported by the host pipeline");
+    if (a.packed && bits == 8) return aeqb::host_fail("packed output needs num_bits 4");
+    if (a.rows * a.cols > 0 && !a.x) return aeqb::host_fail("x is NULL");
+    v[static_cast<size_t>(i)] = HostJob{a.x, a.rows, a.cols, a.q, a.packed, a.scale, a.zp, nullptr};
+  }
+  return run_host(v.data(), n_jobs, 0, bits, 1, 0, k);
 }
 
 int aeqb_host_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs, int block,

@@ -155,6 +155,10 @@ AEQB_API int aeqb_host_requant_rows_batch_f32(const aeqb_rows_job* jobs, int64_t
                                               int symmetric);
 AEQB_API int aeqb_host_requant_blocks_batch_f32(const aeqb_blocks_job* jobs, int64_t n_jobs,
                                                 int block, int bits);
+/* MSE per channel (mse.get_tensor_quant_params, algorithms/uniform_quantize/mse.py:36-128) through the same
+ * pipeline: scale = k * sqrt(mean(row^2)), zero point 0, symmetric; rows must be a multiple of 128 columns
+ * and at most 96 KiB (the fused tile-stream kernel's RMS statistic). */
+AEQB_API int aeqb_host_requant_mse_rows_batch_f32(const aeqb_rows_job* jobs, int64_t n_jobs, int bits, float k);
 /* Which GPUs of the node the host-buffer calls above fan out over (chunks are dealt round-robin,
  * every device has its own ring of slots, streams and staging workers).  n == 0 restores the
  * default: the calling thread's current device only — under one-process-per-GPU launchers every

@@ -198,3 +198,35 @@ def test_model_over_2gb_writes_external_buffers(cuda):
   for i, w in enumerate(ws):
     t = _tensor(m.subgraphs[0], b"layer%d/w" % i)
     np.testing.assert_array_equal(fu.get_tensor_data(t, m.buffers), O.minmax_requant(w, 8, True)["q"])
+
+
+def test_mse_weights_go_through_the_batched_driver(cuda):
+  """SURVEY.md §8f row 1 beyond min-max: MSE per-channel weights with 128-multiple rows travel through
+  the host pipeline in ONE batched call (aeqb_host_requant_mse_rows_batch_f32) and land in the cache;
+  the result equals the per-op path (mse.get_tensor_quant_params) bit for bit; a weight the batched path
+  cannot take (96 columns) is left to the per-op path."""
+  import types
+  from aeq_b200 import host, qtyping, quantizer
+  from aeq_b200.algorithm_manager import AlgorithmName
+  from aeq_b200.algorithms.uniform_quantize import mse
+  from aeq_b200.utils import tfl_flatbuffer_utils as fu
+  from aeq_b200.utils import tfl_model as T
+  # 256-, 48- and 256-column rows: the middle one is not a multiple of 128
+  ws = [O.synthetic_weight(48, 256, 1), O.synthetic_weight(256, 48, 2), O.synthetic_weight(128, 256, 3)]
+  data = T.write_model_to_bytes(tfl_fixtures.fc_stack(ws))
+  qz = quantizer.Quantizer(data)
+  qz.add_weight_only_config(".*", qtyping.TFLOperationName.FULLY_CONNECTED, 8, algorithm_key=AlgorithmName.MSE)
+  m = T.read_model_from_bytes(qz.quantize().quantized_model)
+  assert qz.prefetch_stats["quantized"] == 2 and qz.prefetch_stats["left_to_per_op_path"] == 1
+  g = m.subgraphs[0]
+  cfg = qtyping.TensorQuantizationConfig(num_bits=8, symmetric=True, granularity=qtyping.QuantGranularity.CHANNELWISE)
+  info = qtyping.OpInfo(types.SimpleNamespace(inputs=[0, 1, -1], outputs=[2]), qtyping.TFLOperationName.FULLY_CONNECTED,
+                        0, qtyping.OpQuantizationConfig(weight_tensor_config=cfg))
+  for i, w in enumerate(ws):
+    want = mse.get_tensor_quant_params(info, cfg, w, None)
+    t = _tensor(g, b"layer%d/w" % i)
+    np.testing.assert_array_equal(t.quantization.scale, want.scale.ravel())
+    np.testing.assert_array_equal(fu.get_tensor_data(t, m.buffers), want.quantized_data)
+    np.testing.assert_allclose(want.scale, O.mse_requant(w, 8)["scale"], rtol=1e-6)
+  with pytest.raises(RuntimeError, match="128"):
+    host.requant_mse_rows([ws[1]], 8, 0.05408)
