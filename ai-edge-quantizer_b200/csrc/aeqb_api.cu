@@ -120,9 +120,38 @@ struct RowsOpts { int bits, symmetric; };
 
 // Runs every job: stream-class jobs are grouped into <= kMaxInlineJobs batches per
 // class (one persistent launch each), the rest go through the generic kernel.
+// Per-channel scales are 4 bytes per row: stored into the peers from the requantisation kernel one
+// row at a time they are one NVLink packet each (13.7 M packets per rank and step for the 8 B-parameter
+// set at N = 8: 8.53 ms per step against 6.66 without the exchange).  So the kernel writes its own
+// copy only and a second, tiny launch on the same stream pushes every job's scale vector to the
+// peers with 16-byte stores.  AEQB_MIRROR_IN_KERNEL=1 restores the in-kernel stores (A/B).
+bool mirror_in_kernel() {
+  static const bool v = getenv("AEQB_MIRROR_IN_KERNEL") && atoi(getenv("AEQB_MIRROR_IN_KERNEL"));
+  return v;
+}
+
 int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, const char* who,
-             const aeqb::PeerMirror* peers = nullptr) {
+             const aeqb::PeerMirror* peers_in = nullptr) {
   const int sms = sm_count();
+  const aeqb::PeerMirror* peers = (peers_in && !mirror_in_kernel()) ? nullptr : peers_in;
+  if (peers_in && peers_in->n > 0 && peers == nullptr) {  // mirror afterwards, whatever kernel a tensor takes
+    if (int rc = run_rows(jobs, n, o, st, who, nullptr)) return rc;
+    std::vector<aeqb::MirrorSpan> spans;
+    long long max_n = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (jobs[i].rows <= 0 || jobs[i].cols <= 0 || !jobs[i].scale) continue;
+      const long long cnt = jobs[i].out_stride ? jobs[i].rows : 1;
+      spans.push_back(aeqb::MirrorSpan{jobs[i].scale, cnt});
+      if (cnt > max_n) max_n = cnt;
+    }
+    if (spans.empty()) return 0;
+    void* d_spans = nullptr;
+    if (int rc = upload_table(spans.data(), spans.size() * sizeof(aeqb::MirrorSpan), st, &d_spans)) return rc;
+    const int rc = check(aeqb::launch_mirror_f32(static_cast<const aeqb::MirrorSpan*>(d_spans),
+                                                 static_cast<int>(spans.size()), max_n, *peers_in, st), who);
+    cudaFreeAsync(d_spans, st);
+    return rc;
+  }
   bool done_class[5] = {false, false, false, false, false};
   if (peers && peers->n > 0) {  // only the tile-stream kernels mirror their scales
     for (int64_t i = 0; i < n; ++i)

@@ -16,6 +16,25 @@ inline cudaError_t count_launch(int n = 1) {
   return cudaGetLastError();
 }
 
+// "Configured once" flags for cudaFuncSetAttribute, which is a PER-DEVICE setting: a process that
+// drives several GPUs (aeqb_host_set_devices, or a caller switching devices) must repeat it on each.
+// A process-wide flag made the first launch on a second device fail with "invalid argument".
+struct PerDevice {
+  bool flags[64] = {};
+  static int current() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1;
+  }
+  bool done() const {
+    const int d = current();
+    return d >= 0 && flags[d];
+  }
+  void set() {
+    const int d = current();
+    if (d >= 0) flags[d] = true;
+  }
+};
+
 constexpr int kMaxInlineJobs = 64;
 
 // Per-channel / per-tensor fused requantisation of [rows, cols] fp32 matrices.
@@ -51,6 +70,16 @@ struct PeerMirror {
   int n;
   long long delta[kMaxPeers];
 };
+// A run of fp32 values that a rank mirrors into its peers' copies of the gathered buffer.
+struct MirrorSpan {
+  float* p;
+  long long n;
+};
+// Copies every span into each peer mapping (address + pm.delta[i]) with 16-byte stores where the
+// alignment allows: one NVLink packet per four scales instead of one per scale.
+cudaError_t launch_mirror_f32(const MirrorSpan* d_spans, int n_spans, long long max_n, const PeerMirror& pm,
+                              cudaStream_t st);
+
 struct RowsBatch {
   RowsJob jobs[kMaxInlineJobs];
   int n_jobs;

@@ -562,19 +562,19 @@ cudaError_t configure_nt() {
 
 template <int CPB>
 cudaError_t cholesky_dmma_impl(double* A, int K, double* linv, int* info, cudaStream_t st, int* launches) {
-  static bool configured = false;
+  static PerDevice configured;
   cudaError_t e;
-  if (!configured) {
+  if (!configured.done()) {
     if ((e = cudaFuncSetAttribute(chol_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDiagSmem))) != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
-  static bool nt_configured = false;
-  if (!nt_configured) {
+  static PerDevice nt_configured;
+  if (!nt_configured.done()) {
     if ((e = configure_nt<4, 2, 1, 8, 0, CPB>()) != cudaSuccess) return e;
     if ((e = configure_nt<4, 2, 1, 8, 1, CPB>()) != cudaSuccess) return e;
     if ((e = configure_nt<4, 4, 4, 2, 1, CPB>()) != cudaSuccess) return e;
-    nt_configured = true;
+    nt_configured.set();
   }
   constexpr size_t smem32 = static_cast<size_t>(2) * (32 + 128) * KLD * 8;
   constexpr size_t smem128 = static_cast<size_t>(2) * (128 + 64) * KLD * 8;  // 128 x 64 tiles

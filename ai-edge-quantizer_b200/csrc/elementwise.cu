@@ -222,4 +222,43 @@ cudaError_t launch_swap_axes(const void* in, long long a, long long b, long long
   return cudaErrorInvalidValue;
 }
 
+
+// ------------------------------------------------------------------ peer mirror of fp32 scale vectors
+namespace {
+__global__ void __launch_bounds__(256)
+    mirror_f32_kernel(const MirrorSpan* __restrict__ spans, const PeerMirror pm) {
+  const MirrorSpan s = spans[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool vec = (reinterpret_cast<uintptr_t>(s.p) & 15) == 0;
+  for (int i = 0; i < pm.n; ++i) vec = vec && (pm.delta[i] & 15) == 0;
+  long long done = 0;
+  if (vec) {
+    const long long nv = s.n >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(s.p);
+    for (long long k = t0; k < nv; k += stride) {
+      const float4 v = __ldcg(p4 + k);
+      for (int i = 0; i < pm.n; ++i)
+        *reinterpret_cast<float4*>(reinterpret_cast<char*>(const_cast<float4*>(p4 + k)) + pm.delta[i]) = v;
+    }
+    done = nv << 2;
+  }
+  for (long long k = done + t0; k < s.n; k += stride) {
+    const float v = __ldcg(s.p + k);
+    for (int i = 0; i < pm.n; ++i)
+      *reinterpret_cast<float*>(reinterpret_cast<char*>(s.p + k) + pm.delta[i]) = v;
+  }
+}
+}  // namespace
+
+cudaError_t launch_mirror_f32(const MirrorSpan* d_spans, int n_spans, long long max_n, const PeerMirror& pm,
+                              cudaStream_t st) {
+  if (n_spans <= 0 || pm.n <= 0) return cudaSuccess;
+  long long gx = (max_n / 4 + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 16) gx = 16;
+  mirror_f32_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_spans)), 256, 0, st>>>(d_spans, pm);
+  return count_launch();
+}
+
 }  // namespace aeqb

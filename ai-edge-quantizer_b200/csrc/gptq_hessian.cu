@@ -811,11 +811,11 @@ cudaError_t launch_hessian_inverse(double* hessian, long long K, double damp, in
     e = launch_cholesky_dmma(A, k, reinterpret_cast<double*>(p + hinv_linv_offset(K)), info, st, &launches);
     if (e != cudaSuccess) return e;
   } else if (k >= two_level_min_k) {
-    static bool panel2_configured = false;
-    if (!panel2_configured) {
+    static PerDevice panel2_configured;
+    if (!panel2_configured.done()) {
       e = cudaFuncSetAttribute(chol_panel2, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholPanel2Smem);
       if (e != cudaSuccess) return e;
-      panel2_configured = true;
+      panel2_configured.set();
     }
     for (int J = 0; J < k; J += CNB) {
       const int jend = J + CNB < k ? J + CNB : k;

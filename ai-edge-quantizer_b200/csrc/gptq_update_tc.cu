@@ -250,15 +250,15 @@ cudaError_t gptq_update_tc_prepare(GptqTcMapsOpaque* out, const float* err_hi, c
                                    const float* h_hi, const float* h_lo, long long R, long long K) {
   static_assert(sizeof(GptqTcMapsOpaque) >= sizeof(GptqTcMaps), "opaque storage too small");
   GptqTcMaps* m = reinterpret_cast<GptqTcMaps*>(out);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(gptq_update_tc_kernel<GU_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(gu_smem_bytes(GU_STAGES)));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gptq_update_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(gu_smem_bytes(2)));
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.set();
   }
   if (!make_map(&m->ehi, err_hi, R, K, GU_BM) || !make_map(&m->elo, err_lo, R, K, GU_BM) ||
       !make_map(&m->hhi, h_hi, K, K, GU_BN) || !make_map(&m->hlo, h_lo, K, K, GU_BN))

@@ -182,11 +182,11 @@ cudaError_t launch_reg(const float* x, long long rows, int cols, int n, float no
                        int sm_count, cudaStream_t st) {
   auto kern = hadamard_rows_reg<G>;
   const int smem = G > 1 ? cols * 4 : 0;
-  static bool configured = false;
-  if (!configured && G > 1) {
+  static PerDevice configured;
+  if (!configured.done() && G > 1) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   // Wide segments keep 4 * G floats per thread in phase 2: smaller CTAs keep more rows in flight.
   const int threads = G >= 8 ? 128 : 256;
@@ -335,12 +335,12 @@ template <int LOG2N>
 cudaError_t launch_tiles_k(const float* x, long long ntiles, float norm, float* out, int sm_count,
                            cudaStream_t st) {
   constexpr int smem = kTileWarps * kTileSmemPerWarp;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(hadamard_tiles<LOG2N>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hadamard_tiles<LOG2N>,
@@ -411,12 +411,12 @@ cudaError_t launch_hadamard_rows(const float* x, long long rows, long long cols,
   }
   if (smem_ok) {
     const int smem = static_cast<int>(cols) * 4;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (!configured.done()) {
       cudaError_t e = cudaFuncSetAttribute(hadamard_rows_smem,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
       if (e != cudaSuccess) return e;
-      configured = true;
+      configured.set();
     }
     const int threads = cols >= 8192 ? 512 : (cols >= 1024 ? 256 : 128);
     long long per_sm = 200000 / (smem + 1024);

@@ -648,12 +648,12 @@ cudaError_t launch_rows_warp_k(const float* x, long long rows, int cols, const O
                                cudaStream_t st) {
   constexpr int W = WarpRowsCfg<NV>::kWarps;
   const size_t smem = static_cast<size_t>(W) * static_cast<size_t>(cols) * 4;
-  static bool configured = false;  // per instantiation; the attribute is idempotent
-  if (!configured) {
+  static PerDevice configured;  // per instantiation; the attribute is idempotent
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(octav_rows_warp<NV, FULL, SKIP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, W * NV * 512);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octav_rows_warp<NV, FULL, SKIP>,

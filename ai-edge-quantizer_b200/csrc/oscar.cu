@@ -600,12 +600,12 @@ cudaError_t launch_oscar_clip(const float* W, long long n, long long d, long lon
     const int seg = pow2_ge(d) < 32 ? 32 : pow2_ge(d);
     const int threads = seg >= 1024 ? 1024 : seg;
     const size_t smem = static_cast<size_t>(seg) * 12;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice attr_done;
+    if (!attr_done.done()) {
       cudaError_t e = cudaFuncSetAttribute(oscar_clip_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kOscarMaxRow * 12);
       if (e != cudaSuccess) return e;
-      attr_done = true;
+      attr_done.set();
     }
     long long grid = n;
     if (grid > static_cast<long long>(sm_count) * 4) grid = static_cast<long long>(sm_count) * 4;

@@ -220,12 +220,12 @@ cudaError_t launch_dwr_scales(const float* x, long long n_groups, long long glen
   if (seg < tile && glen != seg) tile = seg;  // a padded short row cannot share a tile
   const int gpt = tile / seg;
   const size_t smem = static_cast<size_t>(tile) * 4 + static_cast<size_t>(gpt) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(dwr_group_scale, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kDwrMaxSeg * 4 + 4096);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.set();
   }
   const long long n_tiles = (n_groups + gpt - 1) / gpt;
   long long grid = n_tiles;

@@ -287,11 +287,11 @@ template <int BLOCK, bool OUT_Q, bool OUT_P, bool MIRROR = false>
 cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
   auto kern = requant_blocks_stream<BLOCK, OUT_Q, OUT_P, MIRROR>;
   const int smem = kStages * kStageBytes;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   long long grid = static_cast<long long>(sm_count) * 2;
   if (grid > b.n_tiles) grid = b.n_tiles;

@@ -571,11 +571,11 @@ template <int STAGE_BYTES, int NW, int SLOTS, int STAGES, bool RICH>
 cudaError_t launch_stream_as(const RowsBatch& b, int sm_count, int ctas_per_sm, cudaStream_t st) {
   auto kern = requant_rows_stream<STAGE_BYTES, NW, SLOTS, STAGES, RICH>;
   const int smem = STAGES * STAGE_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   long long grid = static_cast<long long>(sm_count) * ctas_per_sm;
   if (grid > b.n_tiles) grid = b.n_tiles;

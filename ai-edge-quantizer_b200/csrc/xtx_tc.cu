@@ -340,12 +340,12 @@ size_t xtx_tc_workspace_bytes(long long T, long long K) { return tc_layout(T, K)
 template <typename OutT>
 cudaError_t launch_xtx_tc(const float* x, long long T, long long K, double alpha, OutT* out,
                           void* ws, int sm_count, const int** flag_out, cudaStream_t st, int lower_tri) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(xtx_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(TC_SMEM_BYTES));
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.set();
   }
   const TcLayout l = tc_layout(T, K);
   unsigned char* p = static_cast<unsigned char*>(ws);

@@ -242,7 +242,7 @@ def test_more_than_64_tensors_travel_as_one_launch(cuda, monkeypatch):
     off += r
   before = lib.aeqb_launch_count()
   device.requant_rows_batch(xs, 8, True, outs=mo, mirror=mirror)
-  assert lib.aeqb_launch_count() - before == 1
+  assert lib.aeqb_launch_count() - before == 2  # the requantisation + the 16-byte-store mirror of the scales
   want = np.concatenate([O.minmax_requant(w, 8, True)["scale"].reshape(-1) for w in ws])
   got = buf.cpu().numpy()
   np.testing.assert_array_equal(got[0], want)

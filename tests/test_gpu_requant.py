@@ -174,12 +174,20 @@ def test_scales_mirrored_into_peer_copies(cuda):
     np.testing.assert_array_equal(got[k], want)
   for w, o in zip(ws, outs):
     np.testing.assert_array_equal(o.q.cpu().numpy(), O.minmax_requant(w, 8, True)["q"])
-  # a tensor that falls to the generic kernel cannot be mirrored: loud error, nothing written
-  odd = _dev(O.synthetic_weight(5, 33, index=3), cuda)
+  # the mirror is a second launch over every job's scale vector (16-byte stores where the alignment
+  # allows, scalar otherwise), so a tensor that falls to the generic kernel is mirrored too, at an
+  # unaligned offset of the gathered buffer
+  odd_w = O.synthetic_weight(5, 33, index=3)
+  odd = _dev(odd_w, cuda)
+  buf.fill_(-1.0)
   o = device.Requantized(torch.empty((5, 33), dtype=torch.int8, device=cuda), None,
-                         buf[0, :5].view(5, 1), torch.empty((5, 1), dtype=torch.int32, device=cuda))
-  with pytest.raises(_lib.AeqbError, match="tile-stream"):
-    device.requant_rows_batch([odd], 8, True, outs=[o], mirror=mirror)
+                         buf[0, 3:8].view(5, 1), torch.empty((5, 1), dtype=torch.int32, device=cuda))
+  device.requant_rows_batch([odd], 8, True, outs=[o], mirror=mirror)
+  torch.cuda.synchronize()
+  got = buf.cpu().numpy()
+  for k in range(3):
+    np.testing.assert_array_equal(got[k, 3:8], O.minmax_requant(odd_w, 8, True)["scale"].reshape(-1))
+    assert (got[k, :3] == -1.0).all() and (got[k, 8:] == -1.0).all()
 
 
 @pytest.mark.gpu
