@@ -35,6 +35,7 @@ constexpr int DLD = DNB + 4;     // row stride of the diagonal block in shared m
 constexpr int LLD = 36;          // same rule for the 32 x 32 side tiles (Li, Tm)
 constexpr int DSB = 32;          // pivot sub-block
 constexpr int KS = 32;           // contraction values per stage
+constexpr int kCholDelay = 4;     // full passes over the trailing matrix every this many 128-column steps
 constexpr int KLD = KS + 4;      // padded stage row: (g * 36 + t) mod 16 distinct over a half warp
 
 __device__ __forceinline__ void dmma_884(double (&d)[2], double a, double b) {
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * NF * WN * 64 >= 128 *
     if (tc_lo == 0 && tc_hi == 1) {
       tr = left;  // the first column tile: every row tile has it
       left = 0;
-    } else if (BM == 128 && BN == 64 && tc_lo == 2) {
+    } else if (BM == 128 && BN == 64 && tc_lo == 2 && tc_hi >= 2 * ((K - base + BM - 1) / BM) - 1) {
       // row tile tr holds column tiles 2 .. 2 tr + 1: tr (tr - 1) tiles lie before it.  Closed form
       // instead of a walk over up to 85 row tiles (a quarter of this kernel's stall samples were the
       // integer instructions of that walk).
@@ -381,6 +382,9 @@ __global__ void __launch_bounds__(WM * WN * 32, (MF * WM * NF * WN * 64 >= 128 *
       while (tr * (tr - 1) > left) --tr;
       while ((tr + 1) * tr <= left) ++tr;
       left -= tr * (tr - 1);
+    } else if (BM == 128 && BN == 64 && tc_lo == 2 && tc_hi == 4) {
+      tr = 1 + (left >> 1);  // one 128-column block: two column tiles in every row tile from the second on
+      left &= 1;
     } else {
       for (;; ++tr) {
         const int cnt = nt_tiles_in_row(tr, BM, BN, tc_lo, tc_hi);
@@ -579,6 +583,9 @@ cudaError_t cholesky_dmma_impl(double* A, int K, double* linv, int* info, cudaSt
   constexpr size_t smem32 = static_cast<size_t>(2) * (32 + 128) * KLD * 8;
   constexpr size_t smem128 = static_cast<size_t>(2) * (128 + 64) * KLD * 8;  // 128 x 64 tiles
   const bool lookahead = getenv("AEQB_CHOL_NO_LOOKAHEAD") == nullptr;
+  int delay = getenv("AEQB_CHOL_DELAY") ? atoi(getenv("AEQB_CHOL_DELAY")) : kCholDelay;
+  if (delay < 1) delay = 1;
+  if (delay > 8) delay = 8;
   SideStream* ss = lookahead ? side_stream(st) : nullptr;
   bool rest_pending = false;
   const double* AJ;
@@ -618,19 +625,32 @@ cudaError_t cholesky_dmma_impl(double* A, int K, double* linv, int* info, cudaSt
         A, K, AJ, K, AJ, K, K, DNB, base, 0, 0, 1);
     ++*launches;
     if (nct > 1) {
-      // the other columns: 128 x 64 tiles, two CTAs per SM (one tile's prologue and epilogue overlap
-      // the other's products)
+      // The other columns: 128 x 64 tiles, two CTAs per SM (one tile's prologue and epilogue overlap the
+      // other's products).  DELAYED: the read-modify-write of the trailing matrix is HBM traffic the
+      // products do not hide (26.8 GB over the 86 steps at K = 11008), so a column block only has to be
+      // current when its turn comes.  Every `delay`-th step updates ALL remaining columns with the last
+      // `delay` panels in one pass (contraction 128 x delay); the steps in between update only the
+      // block column the next step's first-column kernel needs, with the panels pending since the last
+      // full pass.  Same products, same order of additions per element within a pass.
+      const int i = J / DNB;
+      const bool full = (i + 1) % delay == 0;
+      const int s0 = full ? i + 1 - delay : (i / delay) * delay;  // first panel not yet applied
+      const int depth = (i - s0 + 1) * DNB;
+      const double* AS = A + static_cast<long long>(s0) * DNB;
       const int nrt = nct, ntc = (below + 63) / 64;
+      const int tc_hi = full ? ntc : (ntc < 4 ? ntc : 4);
       long long ntiles = 0;
-      for (int tr = 0; tr < nrt; ++tr) ntiles += nt_tiles_in_row(tr, 128, 64, 2, ntc);
+      for (int tr = 0; tr < nrt; ++tr) ntiles += nt_tiles_in_row(tr, 128, 64, 2, tc_hi);
       cudaStream_t rs = st;
       if (ss != nullptr) {
         rs = ss->s;
         if ((e = cudaStreamWaitEvent(rs, ss->panel, 0)) != cudaSuccess) return e;
       }
-      chol_nt<4, 4, 4, 2, 1, CPB><<<static_cast<unsigned>(ntiles), 256, smem128, rs>>>(
-          A, K, AJ, K, AJ, K, K, DNB, base, 0, 2, ntc);
-      ++*launches;
+      if (ntiles > 0) {
+        chol_nt<4, 4, 4, 2, 1, CPB><<<static_cast<unsigned>(ntiles), 256, smem128, rs>>>(
+            A, K, AS, K, AS, K, K, depth, base, 0, 2, tc_hi);
+        ++*launches;
+      }
       if (ss != nullptr) {
         if ((e = cudaEventRecord(ss->rest, rs)) != cudaSuccess) return e;
         rest_pending = true;
