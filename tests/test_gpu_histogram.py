@@ -104,7 +104,9 @@ def test_histogram_calibration_func_vs_reference_class(cuda):
     assert set(new) == {"input", "output"} and int(new["input"]["num_samples"]) == 8
     for name in new:
       qsv[name] = upd(qsv.get(name, {}), new[name])
-    want_h.add(x)
+    hj = ref_hu.DynamicHistogram(max_tensor_bins=2048)  # the reference, batch by batch: add, then merge
+    hj.add(x)
+    want_h.merge(hj)
     with np.errstate(all="ignore"):
       fin = x[(x > -3e38) & (x < 3e38)]
       one = {"min": np.reshape(fin.min(), (1, 1)), "max": np.reshape(fin.max(), (1, 1))}
@@ -116,7 +118,8 @@ def test_histogram_calibration_func_vs_reference_class(cuda):
   assert np.float32(got["bin_width"]) == np.float32(want["bin_width"])
   np.testing.assert_array_equal(qsv["input"]["min"], want_mm["min"])
   np.testing.assert_array_equal(qsv["input"]["max"], want_mm["max"])
-  # materialisation: percentile 100 == min-max on the same QSV; 99 narrows the range
+  # materialisation: percentile 100 == min-max on the same QSV; a central 60 % of the mass is narrower
+  # than the moving-average min / max and narrows the range
   cfg = qtyping.TensorQuantizationConfig(8, symmetric=False)
   info = synthetic_graph.op_info(op, None)
   from aeq_b200.algorithms.uniform_quantize import naive_min_max_quantize as nmm
@@ -124,7 +127,7 @@ def test_histogram_calibration_func_vs_reference_class(cuda):
   base = nmm.get_tensor_quant_params(info, cfg, None, {k: qsv["input"][k] for k in ("min", "max")})
   np.testing.assert_array_equal(p100.scale, base.scale)
   np.testing.assert_array_equal(p100.zero_point, base.zero_point)
-  hc.set_percentile(99.0)
+  hc.set_percentile(60.0)
   try:
     p99 = hc.get_tensor_quant_params(info, cfg, None, qsv["input"])
   finally:
