@@ -176,7 +176,7 @@ __device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const floa
 // the RMS row statistic of MSE and the clamped tight pass 2 of clipped / given-scale rows.  The
 // launcher picks the instantiation per batch.
 template <int STAGE_BYTES, int NW, int SLOTS, int STAGES, bool RICH>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW == 4 ? 4 : (NW == 8 ? 2 : 1)))
+__global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (STAGE_BYTES <= 32768 ? 2 : 1)))
     requant_rows_stream(const __grid_constant__ RowsBatch b) {
   static_assert(STAGE_BYTES / (kChunk * 4) == NW * SLOTS, "chunks per warp");
   static_assert(SLOTS <= 32, "one finalising lane per chunk slot");
@@ -649,6 +649,14 @@ int rows_job_class(const RowsJob& j, int bits) {
       best = k;
     }
   }
+  // A row that fills a class-1 stage exactly (4096 floats) ties between class 1 (four CTAs of one row)
+  // and class 2 (two CTAs of two rows).  Measured at the end of round 2 (tools/shape_bench.py,
+  // tools/sustain_probe.py, same box, back to back): class 2 is 0.5 % faster at the full SM clock,
+  // 2.7 % over a 2 GB stack and 3.5 % once the power cap has pulled the clock down (half as many tile
+  // round trips per byte leave more issue slots for the arithmetic).  AEQB_ROWS_TIE_SMALL=1 restores
+  // the old rule.
+  static const bool tie_small = getenv("AEQB_ROWS_TIE_SMALL") && atoi(getenv("AEQB_ROWS_TIE_SMALL"));
+  if (best == 1 && !tie_small && row_bytes == 16384 && min_stream_class() <= 2) best = 2;
   return best;
 }
 
@@ -658,7 +666,13 @@ cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_cou
                                        cudaStream_t st) {
   if (b.n_tiles <= 0) return cudaSuccess;
   if (klass == 1) return launch_stream<16384, 4, 8, 3>(b, sm_count, 4, st);
-  if (klass == 2) return launch_stream<32768, 8, 8, 3>(b, sm_count, 2, st);
+  if (klass == 2) {
+    // AEQB_ROWS_CLASS2_W4=1 (experiment): four consumer warps with 16 chunk slots each instead of eight
+    // with 8 -- half as many (warp, tile) round trips per byte.
+    static const bool w4 = getenv("AEQB_ROWS_CLASS2_W4") && atoi(getenv("AEQB_ROWS_CLASS2_W4"));
+    if (w4) return launch_stream<32768, 4, 16, 3>(b, sm_count, 2, st);
+    return launch_stream<32768, 8, 8, 3>(b, sm_count, 2, st);
+  }
   if (klass == 3) return launch_stream<65536, 16, 8, 3>(b, sm_count, 1, st);
   return launch_stream<98304, 16, 12, 2>(b, sm_count, 1, st);
 }

@@ -321,8 +321,20 @@ class Ctx:
     torch = self.torch
     gen = torch.Generator(device=self.dev).manual_seed(seed)
     out = []
+    # ONE allocation for the whole set, the tensors are views into it — the layout a model's weights have
+    # in its flatbuffer (and one large mapping instead of hundreds of 64 MiB ones);
+    # AEQB_BENCH_SEPARATE_ALLOCS=1 allocates every tensor on its own
+    flat = None
+    if not os.environ.get("AEQB_BENCH_SEPARATE_ALLOCS"):
+      flat = torch.empty(sum(r * c for r, c in shapes), dtype=torch.float32, device=self.dev)
+    off = 0
     for r, c in shapes:
-      w = torch.randn(r, c, device=self.dev, generator=gen) * 0.02
+      if flat is None:
+        w = torch.randn(r, c, device=self.dev, generator=gen) * 0.02
+      else:
+        w = flat[off:off + r * c].view(r, c)
+        off += r * c
+        w.normal_(0.0, 0.02, generator=gen)
       w.view(-1)[::1024] *= 20.0
       out.append(w)
     return out
@@ -386,7 +398,12 @@ def run_fc4096(ctx, steps, warmup):
   mirror, mirror_note = peer_buffer(ctx, T * ROWS, _t.float32)
   flat = mirror.local[:T * ROWS] if mirror is not None else torch.empty(T * ROWS, dtype=torch.float32, device=dev)
   gathered = torch.empty(world * T * ROWS, dtype=torch.float32, device=dev) if world > 1 else None
-  r8 = [device.Requantized(torch.empty((ROWS, COLS), dtype=torch.int8, device=dev), None,
+  if os.environ.get("AEQB_BENCH_SEPARATE_ALLOCS"):
+    q_of = lambda i: torch.empty((ROWS, COLS), dtype=torch.int8, device=dev)
+  else:
+    q_flat = torch.empty(T * ROWS * COLS, dtype=torch.int8, device=dev)
+    q_of = lambda i: q_flat[i * ROWS * COLS:(i + 1) * ROWS * COLS].view(ROWS, COLS)
+  r8 = [device.Requantized(q_of(i), None,
                            flat[i * ROWS:(i + 1) * ROWS].view(ROWS, 1),
                            torch.empty((ROWS, 1), dtype=torch.int32, device=dev)) for i in range(T)]
 
@@ -483,7 +500,7 @@ def run_fc4096(ctx, steps, warmup):
       "scale_exchange_matches_nccl_all_gather": exchange_ok, "peer_mapping_error": mirror_note,
       "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s",
                    "frac": achieved / ctx.peak, "traffic": traffic, "traffic_source": traffic_src,
-                   "kernel": "requant_rows_stream<16384,4,8,3,false>", "bytes_per_weight": 5.0,
+                   "kernel": "requant_rows_stream<32768,8,8,3,false> (two 4096-float rows per 32 KiB tile, 8 consumer warps, 2 CTAs per SM)", "bytes_per_weight": 5.0,
                    "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": k_ms,
                    "launches_per_step": launches_per_step, "peak_source": ctx.peak_src, "timed": timed_how,
                    "relaunched_after_timed_region": {
