@@ -95,6 +95,7 @@ struct RowsBatch {
                                 // producer's walk over hundreds of small tensors reads these, not the jobs
   int rich;
   int one_poller;  // AEQB_ROWS_ONE_POLLER: only consumer warp 0 polls the full barrier, the others park on a named barrier
+  int fold;        // per-row partial maxima folded in registers, no shared-memory atomics (launcher sets it)
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
 int rows_job_class(const RowsJob& j, int bits);

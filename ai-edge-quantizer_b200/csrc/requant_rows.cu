@@ -185,6 +185,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ StageDesc desc[STAGES];
   __shared__ RowAcc s_acc[3][kMaxRowsPerTile];
+  __shared__ __align__(16) unsigned s_part[3][SLOTS][NW];  // FOLD: per-warp |x| maxima of each row of the tile
   __shared__ float2 s_by[NW][SLOTS];  // per-warp (scale, reciprocal) of each chunk slot
   __shared__ double s_sq[RICH ? 3 : 1][RICH ? NW * SLOTS : 1];  // MSE: per-chunk fp64 sums of fp32 squares
 
@@ -284,7 +285,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
     const bool full_tile = nchunks == NW * SLOTS;
     const bool plain = abs_scan && !given && !mse;
     float4 v[SLOTS];
-    if (plain && full_tile) {  // branch-free common case
+    // FOLD: when a row's chunks are a multiple of the consumer warps (4096 / 8192-float rows), every warp
+    // holds the same slots of every row (slot j -> row j / spr), so it folds its slots of a row in
+    // registers and publishes ONE partial maximum per row with a plain store; the finalising lane
+    // maxes the NW partials.  No shared-memory atomics (a sixth of the executed instructions of the
+    // 477-tensor launch went into the per-chunk atomicMax and its divergence region).  The earlier
+    // attempt at this (round 1: slower at the full clock) kept the atomics; what matters now is the
+    // issue-bound regime the power cap puts the kernel in.  AEQB_ROWS_NO_FOLD=1 for A/B runs.
+    const int spr = cpr / NW;
+    const bool fold = b.fold != 0 && plain && full_tile && cpr % NW == 0 && (spr == SLOTS || 2 * spr == SLOTS);
+    if (fold) {
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) v[j] = t4[(warp + j * NW) * 32 + lane];
+      if (spr == SLOTS) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) a = absmax4(a, v[j]);
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
+        if (lane == 0) s_part[buf][0][warp] = m;
+      } else {
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SLOTS / 2; ++j) {
+          a0 = absmax4(a0, v[j]);
+          a1 = absmax4(a1, v[j + SLOTS / 2]);
+        }
+        const unsigned m0 = __reduce_max_sync(0xffffffffu, __float_as_uint(a0));
+        const unsigned m1 = __reduce_max_sync(0xffffffffu, __float_as_uint(a1));
+        if (lane == 0) {
+          s_part[buf][0][warp] = m0;
+          s_part[buf][1][warp] = m1;
+        }
+      }
+    } else if (plain && full_tile) {  // branch-free common case
       // (Measured SLOWER on B200, 0.85-0.91 vs 0.92 of peak: folding the per-chunk atomics into
       //  one divergent region per tile; folding the chunks of a row in registers before one
       //  REDUX + atomic per row; sleeping between mbarrier polls.  The pass-1 -> barrier -> pass-2
@@ -394,6 +427,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
     // the row's first chunk owner publishes scale / zp to global memory.
     RowQ mine;
     mine.b = 1.0f; mine.y = 1.0f; mine.zp = 0.0f; mine.mode = kFastSym;  // unused slots must not veto the tight path
+    auto row_amax = [&](int r) -> float {  // |x| maximum of row r of this tile
+      if (!fold) return __uint_as_float(s_acc[buf][r].amax_bits);
+      unsigned m = 0u;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) m = max(m, s_part[buf][r][w]);
+      return __uint_as_float(m);
+    };
     if (my_valid) {
       const int r = static_cast<int>((static_cast<unsigned>(my_c) * magic) >> 20);
       const long long grow = row0 + r;
@@ -404,7 +444,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
         for (int k2 = 0; k2 < cpr; ++k2) t += s_sq[buf][cfirst + k2];
         const float mean = __fdiv_rn(static_cast<float>(t), static_cast<float>(cols));
         const float sc = __fmul_rn(jcopy.mse_k, __fsqrt_rn(mean));
-        xmax = __uint_as_float(s_acc[buf][r].amax_bits);
+        xmax = row_amax(r);
         const DivBy dv = make_div(sc, xmax);
         mine.b = sc; mine.y = dv.y; mine.zp = 0.0f;
         mine.mode = dv.fast ? kFastClamp : kSlow;
@@ -414,7 +454,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
         }
       } else {
       if (gscale) {
-        mx = __uint_as_float(s_acc[buf][r].amax_bits);  // finalize_row only uses xmax here
+        mx = row_amax(r);  // finalize_row only uses xmax here
         mn = -mx;
         xmax = mx;
       } else if (given) {
@@ -422,7 +462,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
         mx = jcopy.given_max[grow * jcopy.mm_stride];
         xmax = INFINITY;  // row not scanned: always take the IEEE divide
       } else if (sym) {
-        mx = __uint_as_float(s_acc[buf][r].amax_bits);
+        mx = row_amax(r);
         mn = -mx;
         xmax = mx;
       } else {
@@ -580,9 +620,11 @@ cudaError_t launch_stream_as(const RowsBatch& b, int sm_count, int ctas_per_sm, 
   long long grid = static_cast<long long>(sm_count) * ctas_per_sm;
   if (grid > b.n_tiles) grid = b.n_tiles;
   static const int one_poller = getenv("AEQB_ROWS_ONE_POLLER") ? atoi(getenv("AEQB_ROWS_ONE_POLLER")) : kRowsOnePollerDefault;
-  if (b.one_poller != one_poller) {
+  static const int fold = (getenv("AEQB_ROWS_NO_FOLD") && atoi(getenv("AEQB_ROWS_NO_FOLD"))) ? 0 : 1;
+  if (b.one_poller != one_poller || b.fold != fold) {
     RowsBatch bb = b;
     bb.one_poller = one_poller;
+    bb.fold = fold;
     kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(bb);
   } else {
     kern<<<static_cast<unsigned>(grid), (NW + 1) * 32, smem, st>>>(b);
