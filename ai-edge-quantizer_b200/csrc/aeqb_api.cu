@@ -152,10 +152,13 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
     cudaFreeAsync(d_spans, st);
     return rc;
   }
+  long long batch_bytes = 0;  // the class of a job depends on the size of the batch it travels in
+  for (int64_t i = 0; i < n; ++i)
+    if (jobs[i].rows > 0 && jobs[i].cols > 0) batch_bytes += jobs[i].rows * static_cast<long long>(jobs[i].cols) * 4;
   bool done_class[5] = {false, false, false, false, false};
   if (peers && peers->n > 0) {  // only the tile-stream kernels mirror their scales
     for (int64_t i = 0; i < n; ++i)
-      if (jobs[i].rows > 0 && jobs[i].cols > 0 && aeqb::rows_job_class(jobs[i], o.bits) == 0)
+      if (jobs[i].rows > 0 && jobs[i].cols > 0 && aeqb::rows_job_class(jobs[i], o.bits, batch_bytes) == 0)
         return fail("%s: tensor %lld ([%lld, %d]) does not take the tile-stream kernel; gather its "
                     "scales with a collective", who, (long long)i, (long long)jobs[i].rows, jobs[i].cols);
   }
@@ -165,7 +168,7 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
     bool rich = false;
     for (int64_t i = 0; i < n; ++i) {
       aeqb::RowsJob j = jobs[i];
-      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != klass) continue;
+      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits, batch_bytes) != klass) continue;
       j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
       j.cpr_magic = static_cast<unsigned>(((1u << 20) + (j.cols / 128) - 1) / (j.cols / 128));
       j.tile0 = n_tiles;
@@ -207,7 +210,7 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
     };
     for (int64_t i = 0; i < n; ++i) {
       aeqb::RowsJob j = jobs[i];
-      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != klass) continue;
+      if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits, batch_bytes) != klass) continue;
       j.rows_per_tile = aeqb::rows_job_rows_per_tile(j, klass);
       j.cpr_magic = static_cast<unsigned>(((1u << 20) + (j.cols / 128) - 1) / (j.cols / 128));
       j.tile0 = b.n_tiles;
@@ -220,7 +223,7 @@ int run_rows(const aeqb::RowsJob* jobs, int64_t n, RowsOpts o, cudaStream_t st, 
   }
   for (int64_t i = 0; i < n; ++i) {
     const aeqb::RowsJob& j = jobs[i];
-    if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits) != 0) continue;
+    if (j.rows <= 0 || j.cols <= 0 || aeqb::rows_job_class(j, o.bits, batch_bytes) != 0) continue;
     if (j.packed && (j.cols % (8 / o.bits) != 0))
       return fail("%s: packed output of a [%lld, %d] tensor would straddle rows; pack separately",
                   who, (long long)j.rows, j.cols);

@@ -98,7 +98,8 @@ struct RowsBatch {
   int fold;        // per-row partial maxima folded in registers, no shared-memory atomics (launcher sets it)
 };
 // 0: generic kernel, 1 / 2 / 3: tile-stream kernel with 16 / 32 / 64 KiB stages.
-int rows_job_class(const RowsJob& j, int bits);
+// `batch_bytes`: fp32 bytes of the whole batch the job travels in (0: unknown / single tensor).
+int rows_job_class(const RowsJob& j, int bits, long long batch_bytes = 0);
 int rows_job_rows_per_tile(const RowsJob& j, int klass);
 cudaError_t launch_requant_rows_stream(const RowsBatch& b, int klass, int sm_count, cudaStream_t st);
 cudaError_t launch_requant_rows_generic(const RowsJob& j, int bits, int symmetric, cudaStream_t st);

@@ -134,11 +134,23 @@ __device__ __forceinline__ float div_row(float x, const RowQ& rq) {
 
 // Pass 2 of a tile whose rows are all symmetric / unclipped / inside the divide window.
 // Branch-free; partial tiles (row length not a multiple of NW chunks, tensor tails) compute their
-// unused chunk slots on zeros and predicate only the store.
-template <bool FULL, bool CLAMP, int NW, int SLOTS>
+// unused chunk slots on zeros and predicate only the store.  OUT = 1: int8 only, 2: packed INT4
+// only, 3: both -- a compile-time choice: with run-time pointer tests every slot issued the other
+// output's seven instructions predicated off (7 of 20 issue slots per chunk slot of the INT8 launch),
+// and the partial-tile variant wrapped the packed half in a divergence-protected branch per slot
+// (packed INT4 on 2560 / 3584 / 5120 / 11008-wide rows: 0.76-0.81 of peak against 0.97 on full tiles).
+__device__ __forceinline__ void stg_u32(void* p, uint32_t v) {
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_u16(void* p, uint32_t v) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(static_cast<unsigned short>(v)) : "memory");
+}
+
+template <bool FULL, bool CLAMP, int NW, int SLOTS, int OUT>
 __device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const float2* by_slots,
                                             int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks,
                                             float lo, float hi) {
+  (void)lane;
 #pragma unroll
   for (int j = 0; j < SLOTS; ++j) {
     const bool valid = FULL || warp + j * NW < nchunks;  // partial tiles: only the store is predicated
@@ -153,18 +165,65 @@ __device__ __forceinline__ void tight_pass2(const float4 (&v)[SLOTS], const floa
       qa.x = fminf(fmaxf(qa.x, lo), hi); qa.y = fminf(fmaxf(qa.y, lo), hi);
       qb.x = fminf(fmaxf(qb.x, lo), hi); qb.y = fminf(fmaxf(qb.y, lo), hi);
     }
-    if (ql) {
+    if (OUT & 1) {
       const uint2 ra = rmagic2(qa, kMagic), rb = rmagic2(qb, kMagic);
-      if (valid) *reinterpret_cast<uint32_t*>(ql + j * NW * kChunk) = bytes4(ra.x, ra.y, rb.x, rb.y);
+      if (valid) stg_u32(ql + j * NW * kChunk, bytes4(ra.x, ra.y, rb.x, rb.y));
     }
-    if (pl) {
+    if (OUT & 2) {
       const uint2 ra = rmagic2(qa, kMagicPlus8), rb = rmagic2(qb, kMagicPlus8);
       // Two bytes per lane, 64 contiguous bytes per warp store: no cross-lane merge on the
       // pass-2 critical path (the nibble order inside the 16 bits is already final).
       const uint32_t h = nibbles4_biased(ra.x, ra.y, rb.x, rb.y) ^ 0x8888u;
-      if (valid) *reinterpret_cast<uint16_t*>(pl + j * NW * (kChunk / 2)) = static_cast<uint16_t>(h);
+      if (valid) stg_u16(pl + j * NW * (kChunk / 2), h);
     }
   }
+}
+
+template <bool CLAMP, int NW, int SLOTS, int OUT>
+__device__ __forceinline__ void tight_pass2_tile(bool full_tile, const float4 (&v)[SLOTS], const float2* by_slots,
+                                                 int8_t* ql, uint8_t* pl, int lane, int warp, int nchunks,
+                                                 float lo, float hi) {
+  if (full_tile) tight_pass2<true, CLAMP, NW, SLOTS, OUT>(v, by_slots, ql, pl, lane, warp, nchunks, lo, hi);
+  else tight_pass2<false, CLAMP, NW, SLOTS, OUT>(v, by_slots, ql, pl, lane, warp, nchunks, lo, hi);
+}
+
+// Shared-memory max reduction by the calling lane only (inline PTX: the compiler does not wrap it in
+// its warp-aggregation sequence, ~10 instructions per call site when only lane 0 is active anyway).
+__device__ __forceinline__ void smem_red_max(unsigned* p, unsigned v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// Pass 1 of a full tile whose rows split evenly over the consumer warps: SPR consecutive chunk slots of
+// every warp belong to one row.  Two independent maxima per row keep the FMNMX chains short.
+template <int SPR, int NW, int SLOTS>
+__device__ __forceinline__ void fold_rows(const float4 (&v)[SLOTS], unsigned (*part)[NW], int warp, int lane) {
+#pragma unroll
+  for (int r = 0; r < SLOTS / SPR; ++r) {
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < SPR; ++k) {
+      if (k & 1) a1 = absmax4(a1, v[r * SPR + k]);
+      else a0 = absmax4(a0, v[r * SPR + k]);
+    }
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(max_nan(a0, a1)));
+    if (lane == 0) part[r][warp] = m;
+  }
+}
+
+template <int NW, int SLOTS>
+__device__ __forceinline__ bool fold_rows_any(int spr, const float4 (&v)[SLOTS], unsigned (*part)[NW], int warp,
+                                              int lane) {
+#define AEQB_FOLD_CASE(S)                                             \
+  if constexpr (SLOTS % S == 0) {                                     \
+    if (spr == S) {                                                   \
+      fold_rows<S, NW, SLOTS>(v, part, warp, lane);                   \
+      return true;                                                    \
+    }                                                                 \
+  }
+  AEQB_FOLD_CASE(1) AEQB_FOLD_CASE(2) AEQB_FOLD_CASE(3) AEQB_FOLD_CASE(4) AEQB_FOLD_CASE(6)
+  AEQB_FOLD_CASE(8) AEQB_FOLD_CASE(12) AEQB_FOLD_CASE(16)
+#undef AEQB_FOLD_CASE
+  return false;
 }
 
 // ------------------------------------------------------------------ TMA tile stream
@@ -285,64 +344,55 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
     const bool full_tile = nchunks == NW * SLOTS;
     const bool plain = abs_scan && !given && !mse;
     float4 v[SLOTS];
-    // FOLD: when a row's chunks are a multiple of the consumer warps (4096 / 8192-float rows), every warp
-    // holds the same slots of every row (slot j -> row j / spr), so it folds its slots of a row in
-    // registers and publishes ONE partial maximum per row with a plain store; the finalising lane
-    // maxes the NW partials.  No shared-memory atomics (a sixth of the executed instructions of the
-    // 477-tensor launch went into the per-chunk atomicMax and its divergence region).  The earlier
-    // attempt at this (round 1: slower at the full clock) kept the atomics; what matters now is the
-    // issue-bound regime the power cap puts the kernel in.  AEQB_ROWS_NO_FOLD=1 for A/B runs.
-    const int spr = cpr / NW;
-    const bool fold = b.fold != 0 && plain && full_tile && cpr % NW == 0 && (spr == SLOTS || 2 * spr == SLOTS);
-    if (fold) {
-#pragma unroll
-      for (int j = 0; j < SLOTS; ++j) v[j] = t4[(warp + j * NW) * 32 + lane];
-      if (spr == SLOTS) {
-        float a = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SLOTS; ++j) a = absmax4(a, v[j]);
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
-        if (lane == 0) s_part[buf][0][warp] = m;
-      } else {
-        float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SLOTS / 2; ++j) {
-          a0 = absmax4(a0, v[j]);
-          a1 = absmax4(a1, v[j + SLOTS / 2]);
-        }
-        const unsigned m0 = __reduce_max_sync(0xffffffffu, __float_as_uint(a0));
-        const unsigned m1 = __reduce_max_sync(0xffffffffu, __float_as_uint(a1));
-        if (lane == 0) {
-          s_part[buf][0][warp] = m0;
-          s_part[buf][1][warp] = m1;
-        }
-      }
-    } else if (plain && full_tile) {  // branch-free common case
-      // (Measured SLOWER on B200, 0.85-0.91 vs 0.92 of peak: folding the per-chunk atomics into
-      //  one divergent region per tile; folding the chunks of a row in registers before one
-      //  REDUX + atomic per row; sleeping between mbarrier polls.  The pass-1 -> barrier -> pass-2
-      //  critical path wants short independent chains, not fewer instructions.)
+    // FOLD: when a row's chunks are a multiple of the consumer warps (cpr = spr * NW: 2048 / 4096 / 8192-float
+    // rows ...), every warp holds the same slots of every row (slot j -> row j / spr), so it folds its slots
+    // of a row in registers and publishes ONE partial maximum per row with a plain store; the finalising
+    // lane maxes the NW partials.  No shared-memory atomics (a sixth of the executed instructions of the
+    // 477-tensor launch went into the per-chunk atomicMax and its divergence region).  AEQB_ROWS_NO_FOLD=1
+    // for A/B runs.  Every other plain tile (row length not a multiple of NW chunks, tensor tails) folds the
+    // RUN of consecutive slots that share a row and merges once per run with a shared-memory reduction
+    // (red.shared: no warp-aggregation code around it); unused chunk slots load zeros and form runs of
+    // their own, which are dropped.  The row index is made provably warp-uniform (lane 0's view of the stage
+    // descriptor), so the run boundaries are uniform branches.
+    const int cpr_u = __shfl_sync(0xffffffffu, cpr, 0);
+    const int spr = cpr_u / NW;
+    bool fold = false;
+    if (plain) {
 #pragma unroll
       for (int j = 0; j < SLOTS; ++j) {
         const int c = warp + j * NW;
-        v[j] = t4[c * 32 + lane];
-        const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
-        if (lane == 0) atomicMax(&s_acc[buf][r].amax_bits, m);
+        v[j] = (full_tile || c < nchunks) ? t4[c * 32 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
-    } else if (plain) {  // partial tile (row length not a multiple of NW chunks, tensor tail)
-      // Branch-free as well: unused chunk slots load zeros (|0| cannot raise a row's maximum)
-      // and only the shared-memory atomic is predicated.  Guarding the whole slot instead put
-      // every REDUX behind divergence-protected branches: 98 executed instructions per chunk
-      // on 11008-wide rows, a quarter of them ISETP / BRA / BSSY / BSYNC.
+      if (b.fold != 0 && full_tile && spr * NW == cpr_u)
+        fold = fold_rows_any<NW, SLOTS>(spr, v, s_part[buf], warp, lane);
+      if (!fold && cpr_u < NW) {
+        // rows shorter than NW chunks: every slot of a warp is a row of its own, nothing to fold --
+        // one REDUX + one shared atomic per slot, branch-free (invalid slots hold zeros and are predicated)
 #pragma unroll
-      for (int j = 0; j < SLOTS; ++j) {
-        const int c = warp + j * NW;
-        const bool valid = c < nchunks;
-        v[j] = valid ? t4[c * 32 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
-        if (lane == 0 && valid) atomicMax(&s_acc[buf][r].amax_bits, m);
+        for (int j = 0; j < SLOTS; ++j) {
+          const int c = warp + j * NW;
+          const int r = static_cast<int>((static_cast<unsigned>(c) * magic) >> 20);
+          const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(absmax4(0.0f, v[j])));
+          if (lane == 0 && (full_tile || c < nchunks)) atomicMax(&s_acc[buf][r].amax_bits, m);
+        }
+      } else if (!fold) {
+        const unsigned magic_u = __shfl_sync(0xffffffffu, magic, 0);
+        const int nrows_u = __shfl_sync(0xffffffffu, nrows, 0);
+        float acc = 0.0f;
+        int run_r = static_cast<int>((static_cast<unsigned>(warp) * magic_u) >> 20);
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+          const int r = static_cast<int>((static_cast<unsigned>(warp + j * NW) * magic_u) >> 20);
+          if (j > 0 && r != run_r) {  // warp-uniform: close the run
+            const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(acc));
+            if (lane == 0 && run_r < nrows_u) smem_red_max(&s_acc[buf][run_r].amax_bits, m);
+            acc = 0.0f;
+            run_r = r;
+          }
+          acc = absmax4(acc, v[j]);
+        }
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(acc));
+        if (lane == 0 && run_r < nrows_u) smem_red_max(&s_acc[buf][run_r].amax_bits, m);
       }
     } else if (RICH && mse) {
       // mse.get_tensor_quant_params (mse.py:100-108): fp32 squares summed in fp64.  A lane adds up
@@ -491,12 +541,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, (STAGE_BYTES <= 16384 ? 4 : (ST
       int8_t* const ql = qp ? qp + warp * kChunk + lane * 4 : nullptr;
       uint8_t* const pl = pp ? pp + ((warp * kChunk + lane * 4) >> 1) : nullptr;
       const float lo_f = static_cast<float>(qr.lo), hi_f = static_cast<float>(qr.hi);
+      // which outputs the job has, as a warp-uniform value (lane 0's view of the stage descriptor)
+      const int outs = __shfl_sync(0xffffffffu, (qp != nullptr ? 1 : 0) | (pp != nullptr ? 2 : 0), 0);
       if (!RICH || all_fast) {
-        if (full_tile) tight_pass2<true, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
-        else tight_pass2<false, false, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        if (outs == 1) tight_pass2_tile<false, NW, SLOTS, 1>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else if (outs == 2) tight_pass2_tile<false, NW, SLOTS, 2>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else if (outs == 3) tight_pass2_tile<false, NW, SLOTS, 3>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
       } else if constexpr (RICH) {
-        if (full_tile) tight_pass2<true, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
-        else tight_pass2<false, true, NW, SLOTS>(v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        if (outs == 1) tight_pass2_tile<true, NW, SLOTS, 1>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else if (outs == 2) tight_pass2_tile<true, NW, SLOTS, 2>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
+        else if (outs == 3) tight_pass2_tile<true, NW, SLOTS, 3>(full_tile, v, s_by[warp], ql, pl, lane, warp, nchunks, lo_f, hi_f);
       }
       __syncwarp();  // s_by[warp] is rewritten next tile
     } else {
@@ -657,6 +711,12 @@ static int min_stream_class() {
 }
 
 // Whole rows per tile of a class (stage bytes / row bytes, capped).
+// AEQB_ROWS_SMALL_TILES=1: the batch-size rule of rows_job_class is off (A/B runs).
+static bool small_tiles_only() {
+  static const bool v = getenv("AEQB_ROWS_SMALL_TILES") && atoi(getenv("AEQB_ROWS_SMALL_TILES"));
+  return v;
+}
+
 static int class_rows_per_tile(int cols, int klass) {
   const long long stage = klass == 1 ? 16384 : (klass == 2 ? 32768 : (klass == 3 ? 65536 : 98304));
   long long rpt = stage / (static_cast<long long>(cols) * 4);
@@ -670,7 +730,7 @@ static int class_rows_per_tile(int cols, int klass) {
 // smaller class (more independent pipelines).  Measured: a 20 KiB row reaches 0.62 of the HBM
 // peak in class 2 (2 CTAs x 20 KiB) and 0.96 in class 4 (4 rows, 80 KiB); a 44 KiB row 0.68 in
 // class 3 (one row per tile) and 1.02 in class 4 (two rows).
-int rows_job_class(const RowsJob& j, int bits) {
+int rows_job_class(const RowsJob& j, int bits, long long batch_bytes) {
   const long long row_bytes = static_cast<long long>(j.cols) * 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(j.x) % 16 == 0) &&
                        (!j.q || reinterpret_cast<uintptr_t>(j.q) % 4 == 0) &&
@@ -684,7 +744,13 @@ int rows_job_class(const RowsJob& j, int bits) {
     long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
     // 64 KiB per round trip saturates HBM with int8 output; the packed INT4 / INT2 pass 2 is
     // longer, so its round trip wants 96 KiB (4096-wide rows: 0.84 of peak in class 1, 0.95 in 4).
-    const long long cap = (j.packed && !j.q) ? 98304 : 65536;
+    // A batch of half a gigabyte or more takes the 96 KiB tiles whatever it writes: measured back to
+    // back on one box (tools/sustain_ab.py, 477 x [4096,4096] INT8), class 4 ran at 1.00-1.02 of the
+    // measured copy peak at the full clock and 0.94-0.95 power-capped, class 2 at 0.92 / 0.96-0.98 and
+    // class 1 at 0.90 flat; below that size the 148-CTA grid of class 4 loses more to its last partial
+    // wave (a single [4096,4096] tensor is 4.6 tiles per CTA) than the larger tiles gain.
+    const bool big_batch = batch_bytes >= (512ll << 20) && !small_tiles_only();
+    const long long cap = ((j.packed && !j.q) || big_batch) ? 98304 : 65536;
     if (bytes > cap) bytes = cap;
     if (bytes > best_bytes) {
       best_bytes = bytes;
