@@ -33,9 +33,13 @@ namespace aeqb {
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;
+// 64 KiB stages, 16 consumer warps, ONE CTA per SM (round 2, measured back to back on one box with
+// tools/sustain_ab.py, SUSTAIN_KIND=blocks, 477 x [4096,4096] INT4 block-32): 0.98 of the measured copy peak
+// over 0.5 s (1.00-1.01 at the full clock, 0.97 power-capped) against 0.947 flat with 32 KiB stages, 8 warps
+// and two CTAs per SM -- fewer, larger bulk copies per byte, as with the 96 KiB tiles of the rows kernel.
+constexpr int kStageBytes = 65536;
 constexpr int kStageFloats = kStageBytes / 4;
-constexpr int kNW = 8;
+constexpr int kNW = 16;
 constexpr int kSlice = 256;  // floats handled by one warp iteration
 
 struct StageDesc {
@@ -74,7 +78,7 @@ __device__ __forceinline__ float group_max_nan(float v) {
 // scales in a private shared-memory strip and sends the strip to every peer as one run of
 // coalesced 4-byte stores (64 B per peer and tile for block 32) instead of 2 bytes at a time.
 template <int BLOCK, bool OUT_Q, bool OUT_P, bool MIRROR>
-__global__ void __launch_bounds__((kNW + 1) * 32, 2)
+__global__ void __launch_bounds__((kNW + 1) * 32, 1)
     requant_blocks_stream(const __grid_constant__ BlocksBatch b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -293,7 +297,7 @@ cudaError_t launch_stream(const BlocksBatch& b, int sm_count, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured.set();
   }
-  long long grid = static_cast<long long>(sm_count) * 2;
+  long long grid = static_cast<long long>(sm_count);  // one CTA (3 x 64 KiB of stages) per SM
   if (grid > b.n_tiles) grid = b.n_tiles;
   kern<<<static_cast<unsigned>(grid), (kNW + 1) * 32, smem, st>>>(b);
   return count_launch();

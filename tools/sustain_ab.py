@@ -17,10 +17,17 @@ flat = torch.empty(n_big * 4096 * 4096, device=dev)
 flat.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(1))
 ws = list(flat.view(n_big, 4096, 4096).unbind(0))
 print({k: v for k, v in os.environ.items() if k.startswith("AEQB_")})
-for name, n, per_win, wins in (("rows64", 64, 20, 40), (f"rows{n_big}", n_big, 3, 40)):
+kind = os.environ.get("SUSTAIN_KIND", "rows")  # rows: INT8 per-channel; blocks: INT4 block-32 packed + fp16 scales
+for name, n, per_win, wins in ((f"{kind}64", 64, 20, 40), (f"{kind}{n_big}", n_big, 3, 40)):
   w = ws[:n]
-  outs = device.requant_rows_batch(w, 8, True)
-  fn = lambda: device.requant_rows_batch(w, 8, True, outs=outs)
+  if kind == "rows":
+    outs = device.requant_rows_batch(w, 8, True)
+    fn = lambda: device.requant_rows_batch(w, 8, True, outs=outs)
+    bpw = 5.0 + 8.0 / 4096
+  else:
+    outs = device.requant_blocks_batch(w, 32, 4)
+    fn = lambda: device.requant_blocks_batch(w, 32, 4, outs=outs)
+    bpw = 4.5625
   fn()
   torch.cuda.synchronize()
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(wins + 1)]
@@ -30,7 +37,7 @@ for name, n, per_win, wins in (("rows64", 64, 20, 40), (f"rows{n_big}", n_big, 3
       fn()
     ev[k + 1].record()
   torch.cuda.synchronize()
-  nbytes = n * (4096 * 4096 * 5 + 4096 * 8)
+  nbytes = n * 4096 * 4096 * bpw
   gbs = [round(nbytes * per_win / ev[k].elapsed_time(ev[k + 1]) / 1e6) for k in range(wins)]
   print(f"{name:10s} alg GB/s first {gbs[:4]} ... last {gbs[-4:]}  mean {sum(gbs) / len(gbs):.0f}")
   del outs
