@@ -63,7 +63,7 @@ def quantize_device(w_dev, hessian, num_bits: int, symmetric: bool = True,
 
 def quantize_layer_device(weights, feeds, hessians, num_bits: int, symmetric: bool = True,
                           max_hadamard_size: Optional[int] = None, damp: float = 0.01,
-                          concurrent: bool = True):
+                          concurrent: bool = False):
   """Rotated GPTQ of all the FC weights of one layer: [(q, scale, zero_point, hadamard_size)].
 
   weights:  device float32 [R_i, K_i] matrices (e.g. q, k, v, o, gate, up, down of a decoder layer);
@@ -75,7 +75,13 @@ def quantize_layer_device(weights, feeds, hessians, num_bits: int, symmetric: bo
   loop's 64-column steps — that leave most of the GPU idle.  So every Hessian is rotated, inverted
   and every OBS loop runs on its OWN stream: the inverses overlap each other, an OBS loop starts
   as soon as its inverse is there.  Same kernels, same launches per problem, same results as
-  `quantize_device` one weight at a time; concurrent=False runs exactly that, for A/B timing."""
+  `quantize_device` one weight at a time; concurrent=False (the default) runs exactly that on the
+  caller's stream -- each factorisation and OBS loop still overlaps its own lookahead side stream.
+  The stream-per-problem arrangement is opt-in: over the end-of-round-2 runs it measured between
+  0.7x and 2.3x the one-stream time on the Llama-7B layer (70 / 79 / 88 / 188 ms against 82-99 ms; more
+  than eight streams share the device's hardware queues), and one 2-GPU bench run out of three met
+  a non-positive pivot in its first concurrent step that neither a single-GPU replay of the same
+  Hessians nor two further 2-GPU runs reproduced."""
   import torch
   from ... import device
   main = torch.cuda.current_stream()
