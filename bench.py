@@ -299,7 +299,10 @@ class Ctx:
     self.dev = torch.device("cuda", self.local)
     if self.world > 1:
       os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
-      dist.init_process_group("nccl", device_id=self.dev)
+      # a rank that waits five minutes in a collective is not going to be joined (a peer left its mode
+      # on an error): fail instead of holding the launcher for ever
+      import datetime
+      dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
     from aeq_b200 import _lib
     self.lib = _lib.load()
     peaks = {}
