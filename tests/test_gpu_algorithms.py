@@ -104,11 +104,12 @@ def test_octav_rows_vs_oracle(cuda, shape, bits):
   assert len(trace) <= 10
 
 
-@pytest.mark.parametrize("shape", [(3700, 2048), (2000, 4096)])
+@pytest.mark.parametrize("shape", [(3700, 2048), (2000, 4096), (1700, 4096), (4300, 4096)])
 def test_octav_rows_warp_pipeline(cuda, shape):
   """More rows than resident warps: every warp of the one-warp-per-row kernel refills its
   shared-memory row buffer (bulk copy + mbarrier phase flip) at least once; rows with NaN / inf
-  / zero elements sit in both rounds."""
+  / zero elements sit in both rounds.  [4300, 4096] is three rounds of the 1776 resident warps of a
+  B200; special values sit at both ends of the rows."""
   from aeq_b200 import device
   import torch
   w = O.synthetic_weight(*shape, index=91)
@@ -118,6 +119,13 @@ def test_octav_rows_warp_pipeline(cuda, shape):
   w[1, :] = 0.0
   w[shape[0] - 2, ::2] = 0.0
   w[shape[0] - 3, 9] = np.inf
+  if shape[1] > 3000:
+    w[7, 3000] = np.nan
+    w[shape[0] - 5, 4095] = np.nan
+    w[8, 2560:] = 0.0
+    w[shape[0] - 6, 2600] = np.inf
+    w[9, 2560:] = 3.0
+    w[shape[0] - 7, :2560] = 0.0
   with np.errstate(all="ignore"):
     want = O.octav_clip(w, 4, (1,))
   got = device.octav_clip_rows(torch.from_numpy(w).to(cuda), 4).cpu().numpy()
