@@ -112,6 +112,29 @@ def test_synthetic_model_roundtrip():
     T.read_model_from_bytes(b"\x00" * 64)
 
 
+def test_external_buffers_bytes_do_not_depend_on_the_allocation(monkeypatch):
+  """External payloads follow the flatbuffer in a bytearray that is allocated WITHOUT a zero fill
+  (tfl_model._uninitialised_bytearray): every byte, alignment gaps included, must be written, so the
+  result equals what a zero-filled and a 0xAA-filled allocation give, and reads back to the payloads."""
+  from tests import tfl_fixtures
+  rng = np.random.default_rng(3)
+  ws = [rng.standard_normal((r, c)).astype(np.float32) for r, c in ((37, 129), (5, 1031), (64, 64), (3, 7))]
+  m = tfl_fixtures.fc_stack(ws)
+  for i, b in enumerate(m.buffers):  # odd payload sizes: gaps of every length behind them
+    if b.data is not None and len(b.data) > 64:
+      b.data = np.asarray(b.data).view(np.uint8)[:len(b.data) - (i % 16)].copy()
+  got = T.write_model_to_bytes(m, external_buffers=True)
+  monkeypatch.setattr(T, "_uninitialised_bytearray", lambda n: bytearray(n))
+  zero = T.write_model_to_bytes(m, external_buffers=True)
+  monkeypatch.setattr(T, "_uninitialised_bytearray", lambda n: bytearray(b"\xaa" * n))
+  dirty = T.write_model_to_bytes(m, external_buffers=True)
+  assert isinstance(got, bytearray) and got == zero == dirty
+  back = T.read_model_from_bytes(got)
+  for a, b in zip(m.buffers, back.buffers):
+    if a.data is not None and len(a.data) > 0:
+      assert bytes(np.asarray(a.data).view(np.uint8)) == bytes(np.asarray(b.data).view(np.uint8))
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="reference tree not mounted")
 def test_reference_fixtures_roundtrip():
   """Every .tflite the reference ships parses and re-serialises to an identical object tree,
