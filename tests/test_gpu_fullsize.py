@@ -75,6 +75,33 @@ def test_bench_stack_64_tensors_rows_sampled_vs_oracle(cuda):
     np.testing.assert_array_equal(outs[i].scale.cpu().numpy(), ref["scale"])
 
 
+@pytest.mark.parametrize("bits,packed", [(8, False), (4, True)])
+def test_large_batch_of_llama_shapes_takes_96k_tiles_bit_exact(cuda, bits, packed):
+  """A batch of >= 512 MiB takes the 96 KiB-tile class whatever it writes (rows_job_class with
+  batch_bytes): rows of 11008 / 5120 / 3584 / 2560 floats leave partial tiles whose row maxima are
+  merged run-wise, 1536-float rows are shorter than the 16 consumer warps' chunks (slot-wise path),
+  6144- and 2048-float rows split evenly over the warps (folded in registers, spr = 3 and 1).  Every
+  tensor of the batch bit-exact against the oracle, INT8 and packed INT4."""
+  import torch
+  from aeq_b200 import device
+  shapes = [(4096, 11008), (4096, 11008), (4096, 5120), (4096, 3584), (900, 2560), (2050, 1536), (1030, 6144),
+            (3000, 2048)]
+  assert sum(r * c * 4 for r, c in shapes) >= 512 << 20
+  ws = [O.synthetic_weight(r, c, index=300 + i) for i, (r, c) in enumerate(shapes)]
+  ws[2][5, :] = 0.0
+  ws[3][0, 7] = np.inf
+  outs = device.requant_rows_batch([torch.from_numpy(w).to(cuda) for w in ws], bits, True, want_q=not packed,
+                                   want_packed=packed)
+  for w, o in zip(ws, outs):
+    with np.errstate(all="ignore"):
+      ref = O.minmax_requant(w, bits, True)
+    np.testing.assert_array_equal(o.scale.cpu().numpy(), ref["scale"])
+    if packed:
+      np.testing.assert_array_equal(o.packed.cpu().numpy(), O.pack_bits(bits, ref["q"]))
+    else:
+      np.testing.assert_array_equal(o.q.cpu().numpy(), ref["q"])
+
+
 def test_bench_stack_64_tensors_blocks_sampled_vs_oracle(cuda):
   from aeq_b200 import _lib, device
   ws = _device_weights(cuda, 64, seed=1001)
