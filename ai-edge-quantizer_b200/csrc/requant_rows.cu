@@ -744,12 +744,14 @@ int rows_job_class(const RowsJob& j, int bits, long long batch_bytes) {
     long long bytes = static_cast<long long>(ctas) * class_rows_per_tile(j.cols, k) * row_bytes;
     // 64 KiB per round trip saturates HBM with int8 output; the packed INT4 / INT2 pass 2 is
     // longer, so its round trip wants 96 KiB (4096-wide rows: 0.84 of peak in class 1, 0.95 in 4).
-    // A batch of half a gigabyte or more takes the 96 KiB tiles whatever it writes: measured back to
-    // back on one box (tools/sustain_ab.py, 477 x [4096,4096] INT8), class 4 ran at 1.00-1.02 of the
-    // measured copy peak at the full clock and 0.94-0.95 power-capped, class 2 at 0.92 / 0.96-0.98 and
-    // class 1 at 0.90 flat; below that size the 148-CTA grid of class 4 loses more to its last partial
-    // wave (a single [4096,4096] tensor is 4.6 tiles per CTA) than the larger tiles gain.
-    const bool big_batch = batch_bytes >= (512ll << 20) && !small_tiles_only();
+    // A batch of 96 MiB or more takes the 96 KiB tiles whatever it writes: measured back to back on one
+    // box (tools/sustain_ab.py, 477 x [4096,4096] INT8), class 4 ran at 1.00-1.02 of the measured copy
+    // peak at the full clock and 0.94-0.95 power-capped, class 2 at 0.92 / 0.96-0.98 and class 1 at 0.90
+    // flat.  Where it starts to pay (tools/class_threshold.py, n x [4096,4096], L2 flushed between
+    // launches, class 2 -> class 4): 64 MiB 23.6 -> 23.6 us, 128 MiB 39.9 -> 35.9, 256 MiB 68.6 -> 64.5,
+    // 512 MiB 123.9 -> 117.8, 1 GiB 236 -> 222 (a single 64 MiB tensor is 4.6 class-4 tiles per CTA: its
+    // last partial wave costs what the larger tiles gain).
+    const bool big_batch = batch_bytes >= (96ll << 20) && !small_tiles_only();
     const long long cap = ((j.packed && !j.q) || big_batch) ? 98304 : 65536;
     if (bytes > cap) bytes = cap;
     if (bytes > best_bytes) {

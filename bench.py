@@ -503,7 +503,7 @@ def run_fc4096(ctx, steps, warmup):
       "scale_exchange_matches_nccl_all_gather": exchange_ok, "peer_mapping_error": mirror_note,
       "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s",
                    "frac": achieved / ctx.peak, "traffic": traffic, "traffic_source": traffic_src,
-                   "kernel": "requant_rows_stream<98304,16,12,2,false> (six 4096-float rows per 96 KiB tile, 16 consumer warps, 1 CTA per SM: the class a batch of >= 512 MiB takes)", "bytes_per_weight": 5.0,
+                   "kernel": "requant_rows_stream<98304,16,12,2,false> (six 4096-float rows per 96 KiB tile, 16 consumer warps, 1 CTA per SM: the class a batch of >= 96 MiB takes)", "bytes_per_weight": 5.0,
                    "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": k_ms,
                    "launches_per_step": launches_per_step, "peak_source": ctx.peak_src, "timed": timed_how,
                    "relaunched_after_timed_region": {

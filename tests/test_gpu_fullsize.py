@@ -77,8 +77,8 @@ def test_bench_stack_64_tensors_rows_sampled_vs_oracle(cuda):
 
 @pytest.mark.parametrize("bits,packed", [(8, False), (4, True)])
 def test_large_batch_of_llama_shapes_takes_96k_tiles_bit_exact(cuda, bits, packed):
-  """A batch of >= 512 MiB takes the 96 KiB-tile class whatever it writes (rows_job_class with
-  batch_bytes): rows of 11008 / 5120 / 3584 / 2560 floats leave partial tiles whose row maxima are
+  """A large batch (>= 96 MiB; this one is 548 MiB) takes the 96 KiB-tile class whatever it writes
+  (rows_job_class with batch_bytes): rows of 11008 / 5120 / 3584 / 2560 floats leave partial tiles whose row maxima are
   merged run-wise, 1536-float rows are shorter than the 16 consumer warps' chunks (slot-wise path),
   6144- and 2048-float rows split evenly over the warps (folded in registers, spr = 3 and 1).  Every
   tensor of the batch bit-exact against the oracle, INT8 and packed INT4."""
